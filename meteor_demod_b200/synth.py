@@ -1,0 +1,170 @@
+"""Synthetic LRPT-like I/Q for tests and bench (not part of the demodulator path).
+
+Recipe (validated there against the reference: it locks at the
+programmed carrier offset and symbol rate): uniform random QPSK symbols, RRC alpha=0.6
+pulse spanning +-8 symbols at 16x the symbol rate, OQPSK = Q delayed by half a symbol,
+rational resampling to fs (x115/576 for 72 ksym/s, x23/128 for 80 ksym/s at fs=230 kS/s),
+unit rms, carrier offset + phase, complex AWGN at the requested Es/N0, then the raw
+formats wavfile.c:58-69 ingests (u8 offset-128, s16, f32 with s16-scaled values).
+"""
+import struct
+from fractions import Fraction
+
+import numpy as np
+
+UP = 16  # samples per symbol of the intermediate signal
+
+
+def rrc_pulse(alpha=0.6, span=8, sps=UP):
+    t = np.arange(-span * sps, span * sps + 1, dtype=np.float64) / sps
+    h = np.empty_like(t)
+    for i, x in enumerate(t):
+        if abs(x) < 1e-12:
+            h[i] = 1 - alpha + 4 * alpha / np.pi
+        elif abs(abs(4 * alpha * x) - 1) < 1e-9:
+            h[i] = alpha / np.sqrt(2) * ((1 + 2 / np.pi) * np.sin(np.pi / (4 * alpha))
+                                         + (1 - 2 / np.pi) * np.cos(np.pi / (4 * alpha)))
+        else:
+            h[i] = (np.sin(np.pi * x * (1 - alpha)) + 4 * alpha * x * np.cos(np.pi * x * (1 + alpha))) / \
+                   (np.pi * x * (1 - (4 * alpha * x) ** 2))
+    return h / np.sqrt(np.sum(h ** 2))
+
+
+def _ratio(fs, symrate):
+    fr = Fraction(int(fs), int(symrate) * UP)
+    return fr.numerator, fr.denominator
+
+
+def baseband(nsamples, symrate=72000, fs=230000, oqpsk=False, seed=1, periodic=False):
+    """Noise-free, carrier-free unit-rms complex baseband at fs, `nsamples` long.
+
+    periodic=True builds a seamlessly tileable period (circular pulse shaping and
+    resampling); nsamples*symrate/fs must then be an integer.
+    """
+    from scipy.signal import resample_poly
+
+    up, down = _ratio(fs, symrate)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if periodic:
+        nsym_f = Fraction(nsamples * int(symrate), int(fs))
+        if nsym_f.denominator != 1:
+            raise ValueError("periodic baseband needs nsamples*symrate/fs integral")
+        nsym = int(nsym_f)
+    else:
+        nsym = int(np.ceil(nsamples * symrate / fs)) + 64
+    bits = rng.integers(0, 2, size=(nsym, 2))
+    sym = (2.0 * bits[:, 0] - 1) + 1j * (2.0 * bits[:, 1] - 1)
+    x = np.zeros(nsym * UP, np.complex128)
+    x[::UP] = sym
+    h = rrc_pulse()
+    if periodic:
+        H = np.fft.fft(np.concatenate([h, np.zeros(x.size - h.size)]))
+        y = np.fft.ifft(np.fft.fft(x) * H)
+        y = np.roll(y, -(h.size // 2))
+    else:
+        y = np.convolve(x, h)[h.size // 2:][: x.size]
+    if oqpsk:
+        y = y.real + 1j * np.roll(y.imag, UP // 2)
+    if periodic:
+        pad = down * 64
+        ypad = np.concatenate([y[-pad:], y, y[:pad]])
+        z = resample_poly(ypad, up, down)
+        off = pad * up // down
+        z = z[off: off + nsamples]
+    else:
+        z = resample_poly(y, up, down)[32: 32 + nsamples]
+    assert z.size == nsamples, (z.size, nsamples)
+    return z / np.sqrt(np.mean(np.abs(z) ** 2))
+
+
+def impair(z, fs=230000, cfo_hz=700.0, phase=0.7, esn0_db=12.0, sps=None, seed=2, n0=0):
+    """Carrier offset/phase + AWGN. Es/N0 refers to symbol energy: noise var = sps/EsN0 per sample."""
+    n = np.arange(n0, n0 + z.size, dtype=np.float64)
+    y = z * np.exp(1j * (2 * np.pi * cfo_hz * n / fs + phase))
+    if esn0_db is not None:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        sps = sps if sps is not None else 230000 / 72000
+        sigma = np.sqrt(sps / (10 ** (esn0_db / 10)) / 2)
+        y = y + sigma * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
+    return y
+
+
+def to_raw(y, bps=16, rms=6000.0, dc=(30.0, -20.0)):
+    """Complex signal -> interleaved raw array in the format `bps` names (wavfile.c:58-69)."""
+    if bps == 16:
+        v = y * rms + (dc[0] + 1j * dc[1])
+        out = np.empty(2 * y.size, np.int16)
+        out[0::2] = np.clip(np.rint(v.real), -32768, 32767)
+        out[1::2] = np.clip(np.rint(v.imag), -32768, 32767)
+        return out
+    if bps == 8:
+        peak = np.max(np.abs(np.concatenate([y.real, y.imag])))
+        v = y * (64.0 / peak)
+        out = np.empty(2 * y.size, np.uint8)
+        out[0::2] = np.clip(np.rint(v.real) + 128, 0, 255)
+        out[1::2] = np.clip(np.rint(v.imag) + 128, 0, 255)
+        return out
+    if bps == 32:
+        v = y * rms + (dc[0] + 1j * dc[1])
+        out = np.empty(2 * y.size, np.float32)
+        out[0::2] = np.rint(v.real)
+        out[1::2] = np.rint(v.imag)
+        return out
+    raise ValueError("bps must be 8, 16 or 32")
+
+
+def make_raw(nsamples, symrate=72000, fs=230000, oqpsk=False, bps=16, seed=1, cfo_hz=700.0,
+             phase=0.7, esn0_db=12.0, rms=6000.0):
+    z = baseband(nsamples, symrate, fs, oqpsk, seed)
+    y = impair(z, fs, cfo_hz, phase, esn0_db, sps=fs / symrate, seed=seed + 1000)
+    return to_raw(y, bps, rms)
+
+
+def wav_header(data_bytes, fs=230000, bps=16, channels=2):
+    """Canonical 44-byte RIFF/WAVE header, the only form wavfile.c:16-49 accepts."""
+    fmt = 3 if bps == 32 else 1
+    return struct.pack("<4sI4s4sIHHIIHH4sI", b"RIFF", 36 + data_bytes, b"WAVE", b"fmt ", 16, fmt, channels,
+                       fs, fs * channels * bps // 8, channels * bps // 8, bps, b"data", data_bytes)
+
+
+def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 72000, seed=7,
+                   esn0_db=12.0, rms=6000.0, device="cuda", out=None):
+    """Build `nstreams` distinct raw streams on the device from one tileable baseband period.
+
+    Stream b = period rolled by a per-stream shift, tiled to nsamples, mixed with a per-stream
+    carrier (multiple of fs/len(period) so tiling stays seamless), own phase, amplitude and noise.
+    Returns a torch tensor [nstreams, 2*nsamples] of the raw dtype. Plumbing only (torch ops).
+    """
+    import torch
+
+    dt = {8: torch.uint8, 16: torch.int16, 32: torch.float32}[bps]
+    P = int(period.size)
+    base = torch.from_numpy(np.ascontiguousarray(period.astype(np.complex64))).to(device)
+    if out is None:
+        out = torch.empty((nstreams, 2 * nsamples), dtype=dt, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rs = np.random.Generator(np.random.PCG64(seed))
+    step = fs / P
+    n = torch.arange(nsamples, device=device, dtype=torch.float64)
+    sigma = float(np.sqrt(sps / (10 ** (esn0_db / 10)) / 2)) if esn0_db is not None else 0.0
+    for b in range(nstreams):
+        shift = int(rs.integers(0, P))
+        cfo = step * int(rs.integers(-int(1500 / step), int(1500 / step) + 1))
+        ph = float(rs.uniform(0, 2 * np.pi))
+        amp = float(rs.uniform(0.6, 1.2))
+        idx = (torch.arange(nsamples, device=device) + shift) % P
+        z = base[idx]
+        rot = torch.exp(1j * (2 * np.pi * cfo / fs * n + ph)).to(torch.complex64)
+        y = z * rot
+        if sigma:
+            y = y + sigma * torch.complex(torch.randn(nsamples, device=device, generator=g),
+                                          torch.randn(nsamples, device=device, generator=g))
+        if bps == 8:
+            v = torch.view_as_real(y * (64.0 / 3.0 * amp)).round() + 128
+            out[b] = v.clamp(0, 255).reshape(-1).to(dt)
+        else:
+            v = torch.view_as_real(y * (rms * amp))
+            v = (v + torch.tensor([30.0, -20.0], device=device)).round().clamp(-32768, 32767)
+            out[b] = v.reshape(-1).to(dt)
+    return out

@@ -1,0 +1,152 @@
+/*
+ * oracle/ref_driver.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Block-API harness around the UNMODIFIED reference sources of
+ * dbdexter-dev/meteor_demod. The reference .c files are #included from where
+ * they lie under /root/reference (passed as -I by oracle/Makefile); nothing of
+ * the reference is copied into this repository. Output of the build goes to
+ * oracle/_ref/ (git-ignored, travels to the GPU box with the snapshot).
+ *
+ * Why a single translation unit: all reference DSP state is file-scope
+ * `static` (pll.c:16-22, timing.c:13-16, agc.c:9-10, demod.c:5). Including the
+ * sources lets the harness read that state for state-parity tests. pll.c and
+ * timing.c reuse the same static names (pll.c:11-17 vs timing.c:9-16), so the
+ * timing.c copy is renamed with the preprocessor while it is included.
+ *
+ * Fresh state: the reference has no re-init for AGC (agc.c:9-10), the OQPSK
+ * `state`/`inphase` function statics (timing.c:43, demod.c:54) or `updown`
+ * (pll.c:112). The python wrapper therefore dlopen()s a private temp copy of
+ * the built .so for every new demodulator instance.
+ */
+#include <complex.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define _freq t_freq
+#define _phase t_phase
+#define _alpha t_alpha
+#define _beta t_beta
+#define update_estimate t_update_estimate
+#define update_alpha_beta t_update_alpha_beta
+#include "dsp/timing.c"
+#undef _freq
+#undef _phase
+#undef _alpha
+#undef _beta
+#undef update_estimate
+#undef update_alpha_beta
+#include "dsp/pll.c"
+#include "dsp/agc.c"
+#include "dsp/filter.c"
+#include "dsp/sincos.c"
+#include "demod.c"
+
+typedef struct {
+	float t_prev, t_phase, t_freq, t_center, t_maxdev, t_alpha, t_beta;
+	float agc_gain, agc_bias_re, agc_bias_im;
+	float p_freq, p_phase, p_alpha, p_beta, p_err, p_fmax;
+	int p_locked, p_locked_once;
+	int flt_idx, flt_size, flt_interp;
+} ref_state_t;
+
+static int g_oqpsk;
+
+void
+ref_init(float pll_bw, float sym_bw, int samplerate, int symrate, int interp,
+         int order, int oqpsk, float freq_max)
+{
+	g_oqpsk = oqpsk;
+	demod_init(pll_bw, sym_bw, samplerate, symrate, interp, order, oqpsk, freq_max);
+}
+
+void
+ref_get_state(ref_state_t *s)
+{
+	s->t_prev = _prev; s->t_phase = t_phase; s->t_freq = t_freq;
+	s->t_center = _center_freq; s->t_maxdev = _freq_max_dev;
+	s->t_alpha = t_alpha; s->t_beta = t_beta;
+	s->agc_gain = _float_gain;
+	s->agc_bias_re = crealf(_float_bias); s->agc_bias_im = cimagf(_float_bias);
+	s->p_freq = _freq; s->p_phase = _phase; s->p_alpha = _alpha; s->p_beta = _beta;
+	s->p_err = _err; s->p_fmax = _fmax;
+	s->p_locked = _locked; s->p_locked_once = _locked_once;
+	s->flt_idx = _rrc_filter.idx; s->flt_size = _rrc_filter.size;
+	s->flt_interp = _rrc_filter.interp_factor;
+}
+
+/* Copy out the polyphase tap banks (filter.c:18-22 layout: coeffs[j*taps+i]). */
+int
+ref_get_taps(float *dst, int cap)
+{
+	int n = _rrc_filter.size * _rrc_filter.interp_factor;
+	if (dst && cap >= n) memcpy(dst, _rrc_filter.coeffs, sizeof(float)*n);
+	return n;
+}
+
+/* Copy out the delay line in chronological order (oldest first). */
+int
+ref_get_history(float *dst_re_im, int cap_samples)
+{
+	int i, n = _rrc_filter.size;
+	if (!dst_re_im || cap_samples < n) return n;
+	for (i=0; i<n; i++) {
+		float complex v = _rrc_filter.mem[(_rrc_filter.idx + i) % n];
+		dst_re_im[2*i] = crealf(v); dst_re_im[2*i+1] = cimagf(v);
+	}
+	return n;
+}
+
+/*
+ * Push `nsamples` raw interleaved I/Q samples through the reference demodulator.
+ * Sample conversion follows wavfile.c:58-69 (u8: byte-128, s16: raw, f32: raw;
+ * no scaling). For every symbol the reference emits (demod.c:42-43 / :76-82)
+ * the harness stores the float symbol, the int8 soft symbol quantised exactly
+ * as main.c:305-306 does, the index of the input sample that produced it and
+ * the value of pll_did_lock_once() after it (main.c:312 gating input).
+ * Returns the number of symbols (also when it exceeds `cap`; extra ones are
+ * counted but not stored).
+ */
+long
+ref_process(const void *raw, long nsamples, int bps,
+            float *sym, int8_t *soft, long long *sample_idx, uint8_t *lock_once,
+            long cap)
+{
+	const uint8_t *u8 = raw; const int16_t *s16 = raw; const float *f32 = raw;
+	int (*demod)(float complex *) = g_oqpsk ? demod_oqpsk : demod_qpsk;
+	long n, nsym = 0;
+
+	for (n=0; n<nsamples; n++) {
+		float complex sample;
+		switch (bps) {
+			case 8:  sample = (int)u8[2*n]-128 + I*((int)u8[2*n+1]-128); break;
+			case 16: sample = s16[2*n] + I*s16[2*n+1]; break;
+			case 32: sample = f32[2*n] + I*f32[2*n+1]; break;
+			default: return -1;
+		}
+		if (demod(&sample)) {
+			if (nsym < cap) {
+				if (sym) { sym[2*nsym] = crealf(sample); sym[2*nsym+1] = cimagf(sample); }
+				if (soft) {
+					soft[2*nsym]   = MAX(-127, MIN(127, crealf(sample)/2));
+					soft[2*nsym+1] = MAX(-127, MIN(127, cimagf(sample)/2));
+				}
+				if (sample_idx) sample_idx[nsym] = n;
+				if (lock_once) lock_once[nsym] = (uint8_t)pll_did_lock_once();
+			}
+			nsym++;
+		}
+	}
+	return nsym;
+}
+
+/* Scalar probes for known-answer tests (sincos.c:13-40, pll.c:154-159, filter.c:71-94). */
+float ref_fast_sin(float x) { return fast_sin(x); }
+float ref_fast_cos(float x) { return fast_cos(x); }
+float ref_lut_tanh(float x) { return lut_tanh(x); }
+float ref_rrc_coeff(int stage_no, unsigned taps, float osf, float alpha) { return rrc_coeff(stage_no, taps, osf, alpha); }
+float ref_cabsf(float re, float im) { return cabsf(re + I*im); }
+float ref_pll_get_freq(void) { return pll_get_freq(); }
+float ref_mm_omega(void) { return mm_omega(); }
+float ref_agc_get_gain(void) { return agc_get_gain(); }
