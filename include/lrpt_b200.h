@@ -1,0 +1,184 @@
+/*
+ * lrpt_b200.h -- C ABI of the B200-native LRPT demodulator hot path.
+ *
+ * Drop-in boundary. The reference (dbdexter-dev/meteor_demod)
+ * has no plugin/FFI interface; its narrowest seam is the per-sample push API
+ *     demod_init / demod_deinit / demod_qpsk / demod_oqpsk         demod.h:29-50
+ * plus the status getters
+ *     pll_get_freq / pll_get_locked / pll_did_lock_once            pll.h:20,27,34
+ *     mm_omega                                                     timing.h:32
+ *     agc_get_gain                                                 agc.h:18
+ * all over process-wide statics, called from the loop in thread_process
+ * (main.c:303-317). A per-sample call into a GPU is untenable, so this ABI replaces
+ * the BODY of that loop with a block call: raw interleaved I/Q bytes in (exactly what
+ * wav_read consumes, wavfile.c:51-80), int8 soft symbols out (exactly what
+ * main.c:305-306 puts in the ring), every symbol, ungated; the host applies the
+ * 512-symbol lock gating of main.c:308-316 using first_lock_symbol.
+ *
+ * Plain C: opaque handle, POD structs, pointers + sizes, int return codes
+ * (0 = ok, negative = error), no global state, no exceptions, no torch types.
+ * A handle owns `nstreams` independent demodulators ("streams" = recordings or
+ * time shards); each keeps the complete state of the reference's statics, so a
+ * stream continues seamlessly across calls and can be checkpointed / handed to
+ * another process or GPU with lrpt_export_state / lrpt_import_state.
+ *
+ * There is no CPU fallback: every entry point that computes needs a CUDA device
+ * and fails with LRPT_ERR_CUDA otherwise.
+ */
+#ifndef LRPT_B200_H
+#define LRPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRPT_ABI_VERSION 1
+
+enum {
+	LRPT_OK        =  0,
+	LRPT_ERR_ARG   = -1,   /* bad argument / unsupported configuration          */
+	LRPT_ERR_CUDA  = -2,   /* CUDA runtime failure (see lrpt_last_error)          */
+	LRPT_ERR_NOMEM = -3,   /* host or device allocation failed                    */
+	LRPT_ERR_CAP   = -4,   /* a stream produced more symbols than `cap`; state is
+	                          still advanced, surplus symbols were counted, not stored */
+	LRPT_ERR_STATE = -5    /* state blob does not match this handle's configuration */
+};
+
+/* Which kernel runs the recurrence. AUTO picks the warp-specialised kernel when the
+ * configuration fits it and the simple one otherwise; results are bit-identical. */
+enum { LRPT_KERNEL_AUTO = 0, LRPT_KERNEL_SIMPLE = 1, LRPT_KERNEL_WS = 2 };
+
+typedef struct lrpt_demod lrpt_demod_t;       /* opaque; owns device buffers + a CUDA stream */
+
+/* Exactly demod_init's arguments (demod.h:29) + the ingest format (wavfile.c:57-72). */
+typedef struct lrpt_params {
+	float   pll_bw;          /* -b, default 1         (demod.h:15)                 */
+	float   sym_bw;          /* SYM_BW 0.00005        (demod.h:14)                 */
+	float   freq_max;        /* rad/symbol; < 0 => FREQ_MAX 0.3 (pll.c:30); main.c:136 converts -d Hz */
+	int32_t samplerate;      /* -s / wav header                                    */
+	int32_t symrate;         /* -r, truncated to int as main.c:187 does            */
+	int32_t interp_factor;   /* -O, default 5                                      */
+	int32_t rrc_order;       /* -f, default 32 (taps = 2*order+1)                  */
+	int32_t oqpsk;           /* -m oqpsk                                           */
+	int32_t bps;             /* 8 (u8 offset-128) | 16 (s16) | 32 (f32)            */
+	int32_t device;          /* CUDA ordinal                                       */
+	int32_t nstreams;        /* independent demodulators in this handle (>= 1)     */
+	int32_t kernel;          /* LRPT_KERNEL_*                                      */
+} lrpt_params_t;
+
+/*
+ * Complete per-stream state = every static of the reference's hot path
+ * (SURVEY.md section 8e). A state blob is this header followed by the FIR delay
+ * line: (taps-1) complex float samples (re,im), oldest first (filter.h:6 in
+ * chronological order).
+ */
+typedef struct lrpt_state {
+	uint32_t magic;              /* 'LRPS' */
+	uint32_t taps;               /* 2*order+1, for validation                    */
+	/* symbol timing: timing.c:13-14, dual-threshold flag timing.c:43            */
+	float    t_phase, t_freq, t_prev;
+	int32_t  t_dual_state;       /* 1 | 2 (OQPSK only)                            */
+	float    oq_inphase;         /* demod.c:54                                    */
+	/* AGC: agc.c:9-10 */
+	float    agc_gain, agc_bias_re, agc_bias_im;
+	/* Costas PLL: pll.c:16-20, sweep direction pll.c:112 */
+	float    p_phase, p_freq, p_err;
+	int32_t  p_locked, p_locked_once, p_updown;
+	/* bookkeeping: totals since creation / import (main.c:291,298,312) */
+	int64_t  nsamples, nsymbols, first_lock_symbol;   /* first_lock_symbol = -1 until locked once */
+} lrpt_state_t;
+
+/* Host-visible status, the values main.c:250-258 prints. */
+typedef struct lrpt_status {
+	float   pll_freq;        /* pll_get_freq(), rad/symbol (rad/half-symbol for OQPSK) */
+	float   mm_omega;        /* mm_omega()                                          */
+	float   agc_gain;        /* agc_get_gain()                                      */
+	int32_t locked;          /* pll_get_locked()                                    */
+	int32_t locked_once;     /* pll_did_lock_once()                                 */
+	int64_t nsamples, nsymbols, first_lock_symbol;
+} lrpt_status_t;
+
+/* ---- lifecycle: replaces demod_init / demod_deinit (demod.h:29,34) ------------- */
+int  lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p);
+void lrpt_destroy(lrpt_demod_t *h);
+/* re-initialise every stream to the state demod_init + fresh statics give */
+int  lrpt_reset(lrpt_demod_t *h);
+
+/* ---- the hot path: replaces the body of main.c:303-317 ------------------------- */
+/*
+ * Single-stream push (stream 0), HOST buffers. raw_iq: nsamples interleaved I,Q
+ * items of the configured format. soft: 2 int8 per symbol, capacity `cap` symbols.
+ * *nsym = symbols produced by this call. *first_lock_symbol = index (counted from
+ * the stream's first symbol ever) of the first symbol after which
+ * pll_did_lock_once() was true, or -1. Synchronous.
+ */
+int  lrpt_process(lrpt_demod_t *h, const void *raw_iq, size_t nsamples,
+                  int8_t *soft, size_t cap, size_t *nsym, long long *first_lock_symbol);
+
+/*
+ * Batch push, HOST buffers: stream s reads nsamples items at
+ * (char*)raw_iq + s*raw_stride and writes symbols at soft + s*soft_stride
+ * (capacity cap symbols each); nsym[s] receives the per-stream count. sym_f32
+ * (may be NULL) receives the unquantised float symbols (2 floats per symbol,
+ * stride symf_stride bytes) for state-level parity tests. Synchronous; host<->device
+ * copies are pipelined with the kernel in slabs.
+ */
+int  lrpt_process_batch(lrpt_demod_t *h, const void *raw_iq, size_t raw_stride, size_t nsamples,
+                        int8_t *soft, size_t soft_stride, size_t cap, uint32_t *nsym,
+                        float *sym_f32, size_t symf_stride);
+
+/*
+ * Batch push, DEVICE buffers (HBM-resident input, e.g. torch tensors' data_ptr()).
+ * Asynchronous on `cuda_stream` (a cudaStream_t passed as void*; NULL = the handle's
+ * own stream). d_nsym: device uint32[nstreams] (may be NULL). Pointers must be
+ * 16-byte aligned and strides multiples of 16. Use lrpt_sync + lrpt_get_counts to
+ * read the counts on the host.
+ */
+int  lrpt_process_batch_device(lrpt_demod_t *h, const void *d_raw_iq, size_t raw_stride,
+                               size_t nsamples, int8_t *d_soft, size_t soft_stride, size_t cap,
+                               uint32_t *d_nsym, float *d_sym_f32, size_t symf_stride,
+                               void *cuda_stream);
+int  lrpt_sync(lrpt_demod_t *h, void *cuda_stream);
+/* per-stream symbol counts of the most recent call (host copy; call after lrpt_sync) */
+int  lrpt_get_counts(lrpt_demod_t *h, uint32_t *nsym, int nstreams);
+
+/* ---- status: replaces pll_get_freq / pll_get_locked / pll_did_lock_once /
+ *      mm_omega / agc_get_gain (pll.h:20-34, timing.h:32, agc.h:18) -------------- */
+int  lrpt_status(lrpt_demod_t *h, int stream, lrpt_status_t *st);
+
+/* ---- state hand-off / checkpoint ------------------------ */
+size_t lrpt_state_size(const lrpt_demod_t *h);       /* bytes of one state blob */
+int  lrpt_export_state(lrpt_demod_t *h, int stream, void *buf, size_t *len);
+int  lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, size_t len);
+
+/* ---- introspection -------------------------------------------------------------- */
+/*
+ * Host-only (needs no CUDA device): what lrpt_create derives from `p`, exactly as
+ * demod_init does (demod.c:8-15): the power-on state, the polyphase tap banks
+ * (returns taps*interp, the count of floats), the loop constants
+ * {t_center, t_maxdev, t_alpha, t_beta, p_alpha, p_beta, p_fmax} (timing.c:21-27,
+ * pll.c:38,43) and the tanh table (pll.c:40-42). Any output pointer may be NULL.
+ */
+int  lrpt_describe(const lrpt_params_t *p, lrpt_state_t *initial_state, float *taps, int taps_cap,
+                   float loop_consts[7], float lut[32]);
+/* polyphase tap banks as filter_init_rrc lays them out (filter.c:18-22): bank j at [j*taps, (j+1)*taps) */
+int  lrpt_get_taps(const lrpt_demod_t *h, float *dst, int cap);   /* returns taps*interp */
+int  lrpt_get_tanh_lut(const lrpt_demod_t *h, float dst[32]);
+/* number of CUDA kernels this handle has launched so far */
+unsigned long long lrpt_launch_count(const lrpt_demod_t *h);
+/* name of the kernel AUTO resolved to ("simple" | "ws") */
+const char *lrpt_kernel_name(const lrpt_demod_t *h);
+const char *lrpt_last_error(const lrpt_demod_t *h);  /* human-readable detail of the last failure */
+const char *lrpt_strerror(int code);
+int  lrpt_abi_version(void);
+
+/* main.c:136 : -d <Hz> to the rad/symbol freq_max argument (negative stays negative) */
+float lrpt_freq_delta_from_hz(float freq_max_delta_hz, float symrate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRPT_B200_H */
