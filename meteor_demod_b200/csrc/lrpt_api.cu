@@ -205,13 +205,16 @@ extern "C" int lrpt_process_batch_device(lrpt_demod_t *h, const void *d_raw_iq, 
 	a.d_raw = d_raw_iq; a.raw_stride = raw_stride; a.nsamples = nsamples;
 	a.d_soft = d_soft; a.soft_stride = soft_stride; a.cap = (unsigned)cap;
 	a.d_symf = d_sym_f32; a.symf_stride = symf_stride;
-	a.d_nsym = h->d_nsym; a.d_out_off = nullptr;
+	a.d_nsym = nullptr; a.d_out_off = h->d_off;              /* cursor doubles as the per-call count */
 	a.first_stream = 0; a.nstreams = h->p.nstreams;
-	int rc = launch(h, a, st);
-	if (rc) return rc;
+	CU(h, cudaMemsetAsync(h->d_off, 0, sizeof(uint32_t)*h->p.nstreams, st));
+	if (nsamples) {
+		int rc = launch(h, a, st);
+		if (rc) return rc;
+	}
 	if (d_nsym)
-		CU(h, cudaMemcpyAsync(d_nsym, h->d_nsym, sizeof(uint32_t)*h->p.nstreams, cudaMemcpyDeviceToDevice, st));
-	CU(h, cudaMemcpyAsync(h->h_counts, h->d_nsym, sizeof(uint32_t)*h->p.nstreams, cudaMemcpyDeviceToHost, st));
+		CU(h, cudaMemcpyAsync(d_nsym, h->d_off, sizeof(uint32_t)*h->p.nstreams, cudaMemcpyDeviceToDevice, st));
+	CU(h, cudaMemcpyAsync(h->h_counts, h->d_off, sizeof(uint32_t)*h->p.nstreams, cudaMemcpyDeviceToHost, st));
 	return LRPT_OK;
 }
 
@@ -289,7 +292,7 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 		a.d_raw = h->d_raw[b]; a.raw_stride = d_raw_pitch; a.nsamples = n;
 		a.d_soft = h->d_soft; a.soft_stride = d_soft_pitch; a.cap = (unsigned)cap;
 		a.d_symf = sym_f32 ? h->d_symf : nullptr; a.symf_stride = d_symf_pitch;
-		a.d_nsym = h->d_nsym; a.d_out_off = h->d_off;
+		a.d_nsym = nullptr; a.d_out_off = h->d_off;
 		a.first_stream = first; a.nstreams = count;
 		if ((rc = launch(h, a, h->stream))) return rc;
 		CU(h, cudaEventRecord(h->ev_done[b], h->stream));
