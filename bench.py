@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LRPT demodulator hot path (contract: task section 4).
+
+A "step" is one pass of the hot path over one batch of synthetic I/Q: B independent
+streams x N samples (QPSK 72 ksym/s at 230 kS/s, 16-bit, RRC order 32, x5 interpolation by
+default = the configuration BASELINE.json's metric is quoted on), every stream demodulated
+from power-on state to int8 soft symbols, bit-exactly as the strict-IEEE reference does.
+
+  value     whole-job input Msamples/s with the raw I/Q already resident in HBM
+            (CUDA events on the launching stream, max over ranks)
+  e2e       the same through the C ABI with HOST (pinned) buffers: H2D of the raw I/Q and
+            D2H of the soft symbols inside the timed region (lrpt_process_batch)
+  roofline  HBM: algorithmic bytes (raw in + soft out) / kernel time vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the reference's own C code (oracle/_ref/libref_fma.so = reference sources with
+            the reference's release flags), one process per host core, on a bounded sample
+            of the same workload.
+
+Multi-GPU (torchrun): streams are sharded across ranks, no data-path collective, weak scaling
+(every rank demodulates B streams); value = all ranks' samples / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (symrate, oqpsk, bps, order, interp, label)
+    "c1": (72000, 0, 16, 32, 5, "QPSK 72ksym/s fs=230kS/s s16 RRC-32 x5 (BASELINE metric config)"),
+    "c2": (80000, 1, 8, 32, 5, "OQPSK 80ksym/s fs=230kS/s u8 RRC-32 x5"),
+    "c3": (72000, 0, 16, 64, 8, "QPSK 72ksym/s fs=230kS/s s16 RRC-64 x8"),
+}
+FS = 230000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=2048, help="independent streams per GPU")
+    ap.add_argument("--samples", type=int, default=1 << 19, help="samples per stream per step")
+    ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target CPU work per core for the baseline")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks sampler --
+
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ CPU reference ---
+
+_CPU_PERIOD = None     # tileable baseband period, built once in the parent before fork
+
+
+def _cpu_worker(args):
+    """One process = one fresh copy of the reference's statics, demodulating one continuous stream
+    (a 4 Mi-sample raw buffer pushed `reps` times, state carried across pushes)."""
+    kind, cfg, seed, nsamples, reps = args
+    from meteor_demod_b200 import synth
+    from oracle import pyoracle
+    symrate, oqpsk, bps, order, interp = cfg
+    rng = np.random.Generator(np.random.PCG64(seed))
+    P = _CPU_PERIOD.size
+    z = np.tile(np.roll(_CPU_PERIOD, int(rng.integers(0, P))), nsamples // P + 1)[:nsamples]
+    y = synth.impair(z, FS, cfo_hz=float(rng.integers(-1500, 1500)), phase=float(rng.uniform(0, 6.28)),
+                     esn0_db=12.0, sps=FS / symrate, seed=seed)
+    raw = synth.to_raw(y, bps)
+    del z, y
+    if kind == "reference":
+        d = pyoracle.Ref(symrate=symrate, oqpsk=oqpsk, bps=bps, order=order, interp=interp, kind="fma")
+    else:
+        d = pyoracle.Oracle(symrate=symrate, oqpsk=oqpsk, bps=bps, order=order, interp=interp)
+    d.process(raw[: 2 * 65536], want_float=False)         # touch code + data once
+    nsym = 0
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        nsym += d.process(raw, want_float=False).nsym
+    dt = time.perf_counter() - t0
+    return nsamples * reps, dt, nsym
+
+
+def usable_cores():
+    """Host threads this container may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0))
+    for quota_f, period_f in (("/sys/fs/cgroup/cpu.max", None),
+                              ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/sys/fs/cgroup/cpu/cpu.cfs_period_us")):
+        try:
+            if period_f is None:
+                quota, period = open(quota_f).read().split()[:2]
+            else:
+                quota, period = open(quota_f).read().strip(), open(period_f).read().strip()
+            if quota not in ("max", "-1"):
+                n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+            break
+        except Exception:
+            continue
+    return n
+
+
+def _cpu_run(kind, cfg, cores, nsamples, reps):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(kind, cfg, 1000 + i, nsamples, reps) for i in range(cores)], chunksize=1)
+    wall = time.perf_counter() - t0
+    tot = sum(r[0] for r in res)
+    slow = max(r[1] for r in res)
+    per_core = float(np.median([r[0] / r[1] for r in res])) / 1e6
+    return tot / slow / 1e6, per_core, wall, slow
+
+
+def cpu_reference(cfg, seconds, cores=None):
+    """Reference C code on the host cores: `cores` concurrent processes (one per usable host
+    thread), each demodulating its own continuous stream; throughput = total samples / slowest
+    process time. A one-pass calibration sizes the timed run to about `seconds` per process."""
+    from meteor_demod_b200 import synth
+    from oracle import pyoracle
+    global _CPU_PERIOD
+    pyoracle.build()
+    kind = "reference" if pyoracle.have_ref("fma") else "port"
+    cores = cores or usable_cores()
+    symrate, oqpsk = cfg[0], cfg[1]
+    if _CPU_PERIOD is None:
+        _CPU_PERIOD = synth.baseband(FS, symrate=symrate, oqpsk=bool(oqpsk), periodic=True, seed=3).astype(np.complex64)
+    nsamples = 1 << 22
+    value, per_core, wall, slow = _cpu_run(kind, cfg, cores, nsamples, 1)
+    reps = int(seconds / max(slow, 1e-3))
+    if reps > 1:
+        value, per_core, wall, slow = _cpu_run(kind, cfg, cores, nsamples, min(reps, 64))
+    else:
+        reps = 1
+    return {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind,
+            "per_core_msps": per_core, "wall_s": wall,
+            "sample": "%d concurrent processes x one stream of %d x %d samples each (%s), timed region = demod only"
+                      % (cores, min(reps, 64), nsamples, "oracle/_ref/libref_fma.so: reference sources, -O3 "
+                         "-march=x86-64-v3 -ftree-vectorize -std=gnu99" if kind == "reference" else "oracle port, strict IEEE")}
+
+
+# ------------------------------------------------------------------ main -----------
+
+def main():
+    a = parse()
+    symrate, oqpsk, bps, order, interp, label = WORKLOADS[a.workload]
+    cfg = (symrate, oqpsk, bps, order, interp)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "%s; %d streams/GPU x %d samples, power-on state each step" % (label, a.streams, a.samples),
+              "streams_per_gpu": a.streams, "samples_per_stream": a.samples, "parity": "bit-exact vs strict-IEEE reference",
+              "l2": "inputs (%.1f GB/GPU) larger than L2" % (a.streams * a.samples * (bps // 4) / 1e9)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        ncfg = max(1, a.steps)
+        vals = []
+        for _ in range(max(0, min(a.warmup, 1))):
+            cpu_reference(cfg, min(a.cpu_seconds, 2.0))
+        for _ in range(ncfg):
+            vals.append(cpu_reference(cfg, a.cpu_seconds))
+        best = max(vals, key=lambda r: r["value"])
+        line = {"impl": "reference", "metric": "IQ Msamples/s", "value": float(np.mean([v["value"] for v in vals])),
+                "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * float(np.mean([v["wall_s"] for v in vals])), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core_msps")},
+                "gpu_launches": 0}
+        line["cpu_baseline"]["value"] = line["value"]
+        line["e2e"] = {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        print(json.dumps(line))
+        return
+
+    cpu_base = None
+    if not a.no_cpu and world == 1:
+        cpu_base = cpu_reference(cfg, a.cpu_seconds)       # before CUDA is initialised (fork)
+
+    import torch
+    import torch.distributed as dist
+    from meteor_demod_b200 import Demod, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the demodulator has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B, N = a.streams, a.samples
+    d = Demod(symrate=symrate, oqpsk=oqpsk, bps=bps, rrc_order=order, interp_factor=interp, nstreams=B,
+              device=local, kernel=a.kernel)
+    period = synth.baseband(FS, symrate=symrate, oqpsk=bool(oqpsk), periodic=True, seed=3).astype(np.complex64)
+    raw = synth.device_streams(period, B, N, bps=bps, sps=FS / symrate, seed=7 + rank, device="cuda")
+    cap = (d.capacity(N) + 7) // 8 * 8
+    soft = torch.empty((B, 2 * cap), dtype=torch.int8, device="cuda")
+    nsym = torch.zeros(B, dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+
+    def step():
+        d.reset(stream=st)                                  # enqueued on st, ordered with the launch
+        d.process_device(raw, soft, nsym=nsym, stream=st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    l0 = d.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    with Clocks(local) as clk:
+        barrier()
+        ev[0].record(st)
+        for i in range(a.steps):
+            step()
+            ev[i + 1].record(st)
+        st.synchronize()
+        barrier()
+    launches = d.launch_count() - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    counts = d.counts().astype(np.int64)
+    value = world * B * N * a.steps / (total_ms * 1e-3) / 1e6
+
+    # correctness tripwire on the benchmarked data itself: stream 0 against the CPU oracle
+    check = None
+    if rank == 0:
+        from oracle import pyoracle
+        o = pyoracle.Oracle(symrate=symrate, oqpsk=oqpsk, bps=bps, order=order, interp=interp)
+        nchk = min(N, 1 << 18)
+        w = o.process(raw[0, : 2 * nchk].cpu().numpy(), want_float=False)
+        got = soft[0, : 2 * w.nsym].cpu().numpy().reshape(-1, 2)
+        check = bool(np.array_equal(got, w.soft))          # causal: the first nchk samples fix these symbols
+
+    # end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        h_raw = torch.empty((B, raw.shape[1]), dtype=raw.dtype, pin_memory=True)
+        h_raw.copy_(raw)
+        h_soft = torch.empty((B, 2 * cap), dtype=torch.int8, pin_memory=True)
+        h_cnt = np.zeros(B, np.uint32)
+        lib = d.lib
+
+        def e2e_step():
+            d.reset()
+            rc = lib.lrpt_process_batch(d.h, h_raw.data_ptr(), h_raw.stride(0) * h_raw.element_size(), N,
+                                        h_soft.data_ptr(), h_soft.stride(0), cap, h_cnt.ctypes.data, None, 0)
+            assert rc == 0, rc
+        for _ in range(max(1, min(a.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": world * B * N * a.steps / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(B * N * (bps // 4)), "d2h_bytes_per_step": int(2 * int(h_cnt.max()) * B + 4 * B),
+               "ms_per_step": 1e3 * dt / a.steps,
+               "matches_device_path": bool(np.array_equal(h_cnt.astype(np.int64), counts))}
+        del h_raw, h_soft
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak = 6650.0
+    kern_ms = float(np.mean(step_ms))
+    alg_bytes = B * N * (bps // 4) + 2.0 * float(counts.sum())          # raw read + soft symbols written, per launch
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(a.workload)
+    except Exception:
+        pass
+    fir_flops = B * N * 4.0 * (2 * order + 1) * interp                   # all-phase FIR, mul and add counted separately
+    line = {"metric": "IQ Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "kernel": d.kernel_name(), "gpu_launches": int(launches), "oracle_check_stream0": check,
+            "symbols_per_step": int(counts.sum()), "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "recurrence/FP32-issue bound, not HBM bound (DESIGN.md section 5); "
+                                 "fp32: %.2f Tinstr/s of all-phase FIR mul+add" % (fir_flops / (kern_ms * 1e-3) / 1e12)},
+            "e2e": e2e}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,9 @@ int  lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p);
 void lrpt_destroy(lrpt_demod_t *h);
 /* re-initialise every stream to the state demod_init + fresh statics give */
 int  lrpt_reset(lrpt_demod_t *h);
+/* same, enqueued on `cuda_stream` (NULL = the handle's stream) without host synchronisation, so it
+ * orders with lrpt_process_batch_device calls on that stream */
+int  lrpt_reset_async(lrpt_demod_t *h, void *cuda_stream);
 
 /* ---- the hot path: replaces the body of main.c:303-317 ------------------------- */
 /*

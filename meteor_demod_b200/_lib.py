@@ -42,6 +42,7 @@ SYMBOLS = {
     "lrpt_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Params)]),
     "lrpt_destroy": (None, [C.c_void_p]),
     "lrpt_reset": (C.c_int, [C.c_void_p]),
+    "lrpt_reset_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lrpt_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]),
     "lrpt_process_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,

@@ -63,11 +63,14 @@ LRPT_DEV void loop_store(const Loop &r, lrpt_state_t &s)
  * so truncation agrees unless q1 lies within 1e-9 of an integer; only then the real
  * __ddiv_rn runs. The result is identical to the division in every case.
  */
+static __device__ __noinline__ double turn_fraction_slow(double x) { return __ddiv_rn(x, kTwoPiD); }
+
 LRPT_DEV float fast_sin(float fx)
 {
 	const double x = (double)__fmul_rn(fx, 65536.0f);
 	double q = __dmul_rn(x, kInvTwoPiD);
-	if (fabs(q - rint(q)) < 1e-9 || !(fabs(q) < 1048576.0)) q = __ddiv_rn(x, kTwoPiD);
+	/* a call keeps the division out of the straight-line path (it is needed about once in 1e9) */
+	if (fabs(q - rint(q)) < 1e-9 || !(fabs(q) < 1048576.0)) q = turn_fraction_slow(x);
 	const int wide = __double2int_rz(q);
 	int v = (int)(short)(wide & 0xffff);       /* int16 wrap, as cvttsd2si + 16-bit store does */
 	const int sign = v;
@@ -113,26 +116,31 @@ LRPT_DEV void agc_apply(Loop &r, float &re, float &im)
 LRPT_DEV void pll_advance(Loop &r)
 {
 	r.p_phase = __fadd_rn(r.p_phase, r.p_freq);
-	if ((double)r.p_phase >= kTwoPiD)
+	/* (double)p >= 2*M_PI  <=>  p >= kTwoPiF for float p: kTwoPiF is the float just above 2*M_PI */
+	if (r.p_phase >= kTwoPiF)
 		r.p_phase = __double2float_rn(__dsub_rn((double)r.p_phase, kTwoPiD));
 }
 
 /* lut_tanh, pll.c:154-159 */
 LRPT_DEV float lut_tanh(const float *lut, float v)
 {
-	if (v > 15.0f) return 1.0f;
-	if (v < -16.0f) return -1.0f;
-	return lut[__float2int_rz(v) + 16];
+	/* v > 15 -> 1 and v < -16 -> -1 coincide with the clamped lookups because
+	 * lut[31] = (float)tanh(15) = 1 and lut[0] = (float)tanh(-16) = -1 exactly. */
+	const int i = min(max(__float2int_rz(v), -16), 15);
+	return lut[i + 16];
 }
+
+static __device__ __noinline__ float fmod_two_pi_slow(float x) { return __double2float_rn(fmod((double)x, kTwoPiD)); }
 
 /* pll_update_estimate -> compute_error + update_estimate, pll.c:100-130,143-152 */
 LRPT_DEV void pll_update(Loop &r, const lrpt_consts_t &c, const float *lut, float i, float q)
 {
 	const float error = __fsub_rn(__fmul_rn(lut_tanh(lut, i), q), __fmul_rn(lut_tanh(lut, q), i));
 
-	/* _phase = fmod(_phase + _alpha*error, 2*M_PI): float sum, double fmod (exact), narrowed */
-	const double ph = (double)__fadd_rn(r.p_phase, __fmul_rn(c.p_alpha, error));
-	r.p_phase = __double2float_rn(fabs(ph) < kTwoPiD ? ph : fmod(ph, kTwoPiD));
+	/* _phase = fmod(_phase + _alpha*error, 2*M_PI): float sum, double fmod (exact), narrowed.
+	 * |x| < 2*M_PI <=> |x| < kTwoPiF for float x, and then fmod returns x itself. */
+	const float ph = __fadd_rn(r.p_phase, __fmul_rn(c.p_alpha, error));
+	r.p_phase = (fabsf(ph) < kTwoPiF) ? ph : fmod_two_pi_slow(ph);
 	r.p_freq = __fadd_rn(r.p_freq, __fmul_rn(c.p_beta, error));
 
 	/* lock detector: float product, double |e|*pole, double sum, narrowed */
@@ -223,6 +231,125 @@ LRPT_DEV bool symbol_event(Loop &r, const lrpt_consts_t &c, const float *lut, in
 	retime(r, c, out_im);
 	pll_update(r, c, lut, out_re, out_im);
 	return true;
+}
+
+/* ================================================================== fast path ==
+ *
+ * symbol_event above is the reference, statement by statement. symbol_fast computes
+ * the SAME values with the common case laid out as one branch-free block (so the
+ * independent chains -- two sin/cos evaluations, the AGC magnitude, the lock
+ * detector, the timing update -- overlap in the pipeline) and reports `false`
+ * whenever one of its shortcuts is not provably exact for the operands at hand;
+ * the caller then restores the loop state and runs symbol_event. Shortcuts:
+ *
+ *  - turn fraction: trunc(x * RN(1/2pi)) instead of trunc(RN(x / 2pi)); identical
+ *    unless the product lies within 1e-9 of an integer (see fast_sin) -> fallback;
+ *  - cabsf: sqrt by one Newton step on rsqrt.approx in double (relative error
+ *    < 2^-43); accepted only if the estimate scaled by (1 -+ 2^-40) rounds to the
+ *    same float, which then equals (float)sqrt(double) because rounding is monotone;
+ *  - fmod(x, 2pi) = x for |x| < 2pi; anything else -> fallback.
+ * Every other operation is the reference's own, with selects instead of branches.
+ */
+
+LRPT_DEV float sincos_poly(int wide)
+{
+	int v = (int)(short)(wide & 0xffff);
+	const int sign = v;
+	v = (v & 0x7fff) - 16384;
+	const int v2 = (v*v) >> 14;
+	int y = 19900 - ((v2*3516) >> 14);
+	y = 16384 - ((v2*y) >> 14);
+	return __fmul_rn((float)(sign < 0 ? -y : y), 6.103515625e-05f);
+}
+
+/* turn fraction of fast_sin's argument; sets `bad` when the division-free form is not provably exact */
+LRPT_DEV int turn_fraction_fast(float fx, bool &bad)
+{
+	const double q = __dmul_rn((double)__fmul_rn(fx, 65536.0f), kInvTwoPiD);
+	bad |= !(fabs(q - rint(q)) >= 1e-9) || !(fabs(q) < 1048576.0);
+	return __double2int_rz(q);
+}
+
+/* (float)sqrt(s) for a double s = x*x + y*y, branch-free; sets `bad` when not provably exact */
+LRPT_DEV float sqrt_to_float_fast(double s, bool &bad)
+{
+	const float sf = __double2float_rn(s);
+	float y0;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(sf));
+	const double y = (double)y0;
+	const double g = s*y;                       /* ~ sqrt(s), relative error < 2^-21.9 */
+	const double h = 0.5*y;
+	const double g1 = fma(g, fma(-g, h, 0.5), g);   /* one Newton step: relative error < 2^-43 */
+	const float lo = __double2float_rn(g1*(1.0 - 0x1p-40));
+	const float hi = __double2float_rn(g1*(1.0 + 0x1p-40));
+	bad |= !(lo == hi) || !(sf > 1e-30f) || !(sf < 1e30f);
+	return lo;
+}
+
+template <bool OQ>
+LRPT_DEV bool symbol_fast(Loop &r, const lrpt_consts_t &c, const float *lut, int half,
+                          float re, float im, float &out_re, float &out_im, bool &emitted)
+{
+	bool bad = false;
+
+	/* pll_mix's oscillator values for the CURRENT phase (pll.c:53-54) */
+	const float nph = -r.p_phase;
+	const float s = sincos_poly(turn_fraction_fast(nph, bad));
+	const float co = sincos_poly(turn_fraction_fast(__double2float_rn(__dadd_rn((double)nph, kHalfPiD)), bad));
+
+	/* agc_apply (agc.c:13-25) */
+	const float keep = 1.0f - 0.001f;
+	r.bias_re = __fadd_rn(__fmul_rn(r.bias_re, keep), __fmul_rn(0.001f, re));
+	r.bias_im = __fadd_rn(__fmul_rn(r.bias_im, keep), __fmul_rn(0.001f, im));
+	const float sr = __fmul_rn(__fsub_rn(re, r.bias_re), r.gain);
+	const float si = __fmul_rn(__fsub_rn(im, r.bias_im), r.gain);
+	const double da = (double)sr, db = (double)si;
+	const float mag = sqrt_to_float_fast(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)), bad);
+	const float g = __fadd_rn(r.gain, __fmul_rn(0.0001f, __fsub_rn(190.0f, mag)));
+	r.gain = (0.0f > g) ? 0.0f : g;
+
+	/* NCO advance (pll.c:61-62), wrap by select */
+	const float p1 = __fadd_rn(r.p_phase, r.p_freq);
+	const float pw = __double2float_rn(__dsub_rn((double)p1, kTwoPiD));
+	const float p2 = (p1 >= kTwoPiF) ? pw : p1;
+
+	if (OQ && half == 1) {                                  /* demod.c:66-71: I arm only */
+		r.oq_inphase = __fsub_rn(__fmul_rn(sr, co), __fmul_rn(si, s));
+		r.p_phase = p2;
+		emitted = false;
+		return !bad;
+	}
+	if (OQ) {                                               /* demod.c:72-83 */
+		out_im = __fadd_rn(__fmul_rn(sr, s), __fmul_rn(si, co));
+		out_re = r.oq_inphase;
+	} else {                                                /* pll_mix, pll.c:60 */
+		out_re = __fsub_rn(__fmul_rn(sr, co), __fmul_rn(si, s));
+		out_im = __fadd_rn(__fmul_rn(sr, s), __fmul_rn(si, co));
+	}
+
+	retime(r, c, out_im);                                   /* timing.c:60-95, already branch-free */
+
+	/* pll_update_estimate (pll.c:100-130) */
+	const float error = __fsub_rn(__fmul_rn(lut_tanh(lut, out_re), out_im), __fmul_rn(lut_tanh(lut, out_im), out_re));
+	const float ph = __fadd_rn(p2, __fmul_rn(c.p_alpha, error));
+	bad |= !(fabsf(ph) < kTwoPiF);                          /* else fmod really reduces */
+	r.p_phase = ph;
+	const float f1 = __fadd_rn(r.p_freq, __fmul_rn(c.p_beta, error));
+	r.p_err = __double2float_rn(__dadd_rn((double)__fmul_rn(r.p_err, 1.0f - 0.001f),
+	                                      __dmul_rn(fabs((double)error), (double)0.001f)));
+	const int was = r.locked;
+	const int acquire = (r.p_err < 85.0f && !was) ? 1 : 0;
+	const int now = acquire ? 1 : ((r.p_err > 105.0f && was) ? 0 : was);
+	r.locked = now;
+	r.locked_once |= acquire;
+	const float fsw = __double2float_rn(__dadd_rn((double)f1, r.updown > 0 ? 0.000001 : -0.000001));
+	const float f2 = now ? f1 : fsw;
+	const int up1 = (f2 <= -c.p_fmax) ? 1 : r.updown;
+	r.updown = (f2 >= c.p_fmax) ? -1 : up1;
+	const float f3 = (c.p_fmax < f2) ? c.p_fmax : f2;
+	r.p_freq = (-c.p_fmax > f3) ? -c.p_fmax : f3;
+	emitted = true;
+	return !bad;
 }
 
 } // namespace lrpt

@@ -25,11 +25,13 @@
 
 namespace lrpt {
 
-constexpr int WS_T        = 64;    /* samples per tile                           */
-constexpr int WS_SLOTS    = 3;     /* FIR tile ring depth                        */
-constexpr int WS_PRODUCERS = 4;    /* producer warps                             */
+constexpr int WS_T        = 32;    /* samples per tile = one FIR unit per stream  */
+constexpr int WS_SLOTS    = 2;     /* FIR tile ring depth                        */
+constexpr int WS_PRODUCERS = 16;   /* producer warps                             */
 constexpr int WS_THREADS  = 32*(1 + WS_PRODUCERS);
 constexpr int WS_MAX_G    = 32;    /* streams per CTA = consumer lanes           */
+constexpr int WS_CTAS_PER_SM = 1;  /* one big CTA per SM: the recurrence warp's time per symbol does not
+                                      depend on how many of its 32 lanes carry a stream, so lanes are filled first */
 constexpr int NCO_CHUNK   = 8;     /* timing sub-steps evaluated per branch      */
 constexpr int WS_MAX_TAPS = 257;
 constexpr int WS_MAX_L    = 8;
@@ -47,7 +49,8 @@ struct WsArgs {
 	uint32_t     *nsym_out, *out_off;
 	int           first_stream, nstreams;
 	int           G;           /* streams per CTA */
-	int           ring;        /* delay-line ring entries per stream (power of two) */
+	int           win;         /* delay-line window entries per stream: H + NT*T */
+	int           NT;          /* tiles per window epoch: 2 + ceil(H/T) */
 };
 
 /* ------------------------------------------------------------- mbarrier ---- */
@@ -92,16 +95,16 @@ template <int L> struct TapPad { static constexpr int value = (L <= 4) ? 4 : 8; 
  * chain: acc = acc + x*h, oldest tap first, multiply and add rounded separately.
  */
 template <int L>
-LRPT_DEV void fir_all_phases(const float2 *__restrict__ ring, int mask, int pos,
-                             const float *__restrict__ hT, int taps, float2 *__restrict__ out)
+LRPT_DEV void fir_all_phases(const float2 *__restrict__ w, const float *__restrict__ hT, int taps,
+                             float2 *__restrict__ out)
 {
 	constexpr int LP = TapPad<L>::value;
 	float ar[L], ai[L];
 #pragma unroll
 	for (int p = 0; p < L; p++) { ar[p] = 0.0f; ai[p] = 0.0f; }
-#pragma unroll 4
+#pragma unroll 8
 	for (int k = 0; k < taps; k++) {
-		const float2 x = ring[(pos + k) & mask];
+		const float2 x = w[k];
 		float hv[LP];
 		*reinterpret_cast<float4 *>(hv) = *reinterpret_cast<const float4 *>(hT + k*LP);
 		if (LP == 8) *reinterpret_cast<float4 *>(hv + 4) = *reinterpret_cast<const float4 *>(hT + k*LP + 4);
@@ -117,8 +120,89 @@ LRPT_DEV void fir_all_phases(const float2 *__restrict__ ring, int mask, int pos,
 
 /* ------------------------------------------------------------- kernel ------ */
 
-template <int L>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+/*
+ * One chunk of advance_timeslot (timing.c:32-38) / advance_timeslot_dual (:41-57):
+ * up to NCO_CHUNK float additions of the NCO step, stopping at the first sum that
+ * reaches the threshold. Fast path (step > 0, at least NCO_CHUNK sub-steps left):
+ * the sums are non-decreasing, so the number of sums below the threshold IS the
+ * index of the first crossing -- no bit scan, no data-dependent branch inside.
+ * Returns true when a crossing was found; Qx = its sub-step index.
+ */
+LRPT_DEV bool nco_chunk(Loop &r, const lrpt_consts_t &c, int &Q, int Qend, int &Qx, int &half)
+{
+	const float f = r.t_freq;
+	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
+	const int limit = Qend - Q;                                     /* >= 1 */
+	bool found;
+	if (f > 0.0f && limit >= NCO_CHUNK) {
+		float ph[NCO_CHUNK];
+		float acc = r.t_phase;
+		int below = 0;
+#pragma unroll
+		for (int j = 0; j < NCO_CHUNK; j++) {
+			acc = __fadd_rn(acc, f);
+			ph[j] = acc;
+			below += (acc >= thr) ? 0 : 1;
+		}
+		float sel = ph[NCO_CHUNK-1];
+#pragma unroll
+		for (int j = NCO_CHUNK - 2; j >= 0; j--) sel = (ph[j] >= thr) ? ph[j] : sel;
+		r.t_phase = sel;                                            /* first sum >= thr, or the last sum */
+		found = below < NCO_CHUNK;
+		Qx = Q + below;
+		Q += found ? below + 1 : NCO_CHUNK;
+	} else {
+		/* end of the block, or a non-positive step from an imported state: one sub-step at a time */
+		found = false;
+		const int n = min(limit, NCO_CHUNK);
+		float acc = r.t_phase;
+		for (int j = 0; j < n && !found; j++) {
+			acc = __fadd_rn(acc, f);
+			Qx = Q; Q++;
+			found = acc >= thr;
+		}
+		r.t_phase = acc;
+	}
+	if (found && c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
+	return found;
+}
+
+/*
+ * Run the timing NCO from sub-step Q to its next crossing, not beyond tile end q1 unless the
+ * crossing search is a single predicted shot. In lock the number of sub-steps between crossings
+ * repeats within +-1, so the previous count `guess` predicts this one: take guess-2 plain adds,
+ * then test only the next three sums. Any surprise (acquisition transients, block end, a guess
+ * that is off) falls back to the exhaustive chunks above, starting again from the untouched
+ * phase. Either way the sums are the reference's float adds, in order.
+ */
+LRPT_DEV bool nco_to_crossing(Loop &r, const lrpt_consts_t &c, int &Q, int q1, int Qend,
+                              int &Qx, int &half, int &guess)
+{
+	const float f = r.t_freq;
+	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
+	const int n = guess - 2;
+	if (f > 0.0f && n >= 0 && Q + n + 3 <= Qend) {
+		float p = r.t_phase;
+		for (int j = 0; j < n; j++) p = __fadd_rn(p, f);
+		const float p1 = __fadd_rn(p, f), p2 = __fadd_rn(p1, f), p3 = __fadd_rn(p2, f);
+		if (!(p >= thr) && p3 >= thr) {
+			const bool h1 = p1 >= thr, h2 = p2 >= thr;
+			const int k = h1 ? 1 : (h2 ? 2 : 3);
+			r.t_phase = h1 ? p1 : (h2 ? p2 : p3);
+			Qx = Q + n + k - 1; Q += n + k; guess = n + k;
+			if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
+			return true;
+		}
+	}
+	const int start = Q;
+	bool found = false;
+	while (!found && Q < q1) found = nco_chunk(r, c, Q, Qend, Qx, half);
+	if (found) guess = Q - start;
+	return found;
+}
+
+template <int L, bool OQ>
+__global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM)
 demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 {
 	constexpr int LP = TapPad<L>::value;
@@ -126,7 +210,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
 	const int taps = c.taps, H = taps - 1;
-	const int ring = a.ring, mask = ring - 1;
+	const int win = a.win, NT = a.NT;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int g0 = blockIdx.x*a.G;                                  /* first stream (launch-local) of this CTA */
 	const int Gc = min(a.G, a.nstreams - g0);                       /* streams this CTA serves */
@@ -137,8 +221,8 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 	uint64_t *empty = full + S;                                     /* [S] */
 	float *lut = reinterpret_cast<float *>(empty + S);              /* [32] */
 	float *hT  = lut + 32;                                          /* [taps][LP] */
-	float2 *rings = reinterpret_cast<float2 *>(hT + ((taps*LP + 3) & ~3));   /* [G][ring] */
-	float2 *tiles = rings + (size_t)a.G*ring;                       /* [G][S][T*L] */
+	float2 *wins  = reinterpret_cast<float2 *>(hT + ((taps*LP + 3) & ~3));   /* [G][win]  delay-line windows */
+	float2 *tiles = wins + (size_t)a.G*win;                         /* [G][S][T*L] FIR outputs */
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < S; s++) { mbar_init(&full[s], P); mbar_init(&empty[s], 1); }
@@ -170,7 +254,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		}
 		const int Qend = a.nsamples*L;          /* total timing sub-steps of this launch */
 		int Q = 0;                              /* sub-steps already taken               */
-		bool have_x = false; int Qx = 0, half = 0;
+		bool have_x = false; int Qx = 0, half = 0, guess = 0;
 		const float2 *my_tiles = tiles + (size_t)lane*S*T*L;
 
 		for (int t = 0; t < ntiles; t++) {
@@ -181,52 +265,29 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 				const int q1 = min((t + 1)*T, a.nsamples)*L;
 				const float2 *tile = my_tiles + slot*T*L;
 				while (true) {
+					/* all lanes first run their timing NCO to the next crossing ... */
 					if (!have_x) {
 						if (Q >= q1) break;
-						/* advance_timeslot x NCO_CHUNK (timing.c:32-38 / :41-57), branch-free */
-						const float f = r.t_freq;
-						const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
-						float ph[NCO_CHUNK];
-						float acc = r.t_phase;
-						unsigned hit = 0;
-#pragma unroll
-						for (int j = 0; j < NCO_CHUNK; j++) {
-							acc = __fadd_rn(acc, f);
-							ph[j] = acc;
-							hit |= (acc >= thr) ? (1u << j) : 0u;
-						}
-						const int limit = Qend - Q;                 /* >= 1 */
-						const int first = __ffs(hit);               /* 1-based, 0 = none */
-						if (first != 0 && first <= limit) {
-							float sel = ph[0];
-#pragma unroll
-							for (int j = 1; j < NCO_CHUNK; j++) sel = (first == j + 1) ? ph[j] : sel;
-							r.t_phase = sel;
-							Qx = Q + first - 1; Q += first; have_x = true;
-							if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
-						} else if (limit >= NCO_CHUNK) {
-							r.t_phase = ph[NCO_CHUNK-1]; Q += NCO_CHUNK;
-						} else {                                     /* end of the block */
-							float sel = ph[0];
-#pragma unroll
-							for (int j = 1; j < NCO_CHUNK; j++) sel = (limit == j + 1) ? ph[j] : sel;
-							r.t_phase = sel; Q += limit;
-						}
+						have_x = nco_to_crossing(r, c, Q, q1, Qend, Qx, half, guess);
 					}
-					if (have_x) {
-						if (Qx >= q1) break;                         /* belongs to a later tile */
-						const float2 y = tile[Qx - q0];              /* filter_get(flt, i), demod.c:35 */
-						float ore, oim;
-						if (symbol_event(r, c, lut, half, y.x, y.y, ore, oim)) {
-							if (r.locked_once && first_lock < 0) first_lock = nsymbols;
-							if (off + nsym < a.cap) {
-								out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
-								if (outf) outf[off + nsym] = make_float2(ore, oim);
-							}
-							nsym++; nsymbols++;
-						}
-						have_x = false;
+					if (!have_x || Qx >= q1) break;                  /* nothing left in this tile */
+					/* ... then take the symbol step together (demod.c:35-43 / :66-83) */
+					const float2 y = tile[Qx - q0];                  /* filter_get(flt, i) */
+					const Loop saved = r;
+					float ore, oim; bool emitted;
+					if (!symbol_fast<OQ>(r, c, lut, half, y.x, y.y, ore, oim, emitted)) {
+						r = saved;                                   /* a shortcut was not provably exact */
+						emitted = symbol_event(r, c, lut, half, y.x, y.y, ore, oim);
 					}
+					if (emitted) {
+						if (r.locked_once && first_lock < 0) first_lock = nsymbols;
+						if (off + nsym < a.cap) {
+							out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
+							if (outf) outf[off + nsym] = make_float2(ore, oim);
+						}
+						nsym++; nsymbols++;
+					}
+					have_x = false;
 				}
 			}
 			__syncwarp();
@@ -248,8 +309,14 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		const int units = Gc*SLABS;                                 /* (stream, 32-sample slab) per tile */
 		constexpr int MAXU = (WS_MAX_G*SLABS + P - 1)/P;
 
-		/* prologue: delay line (taps-1 samples of history) + tile 0 into the rings.
-		 * ring position of sample m is (m + H) & mask. */
+		/*
+		 * Delay-line window of stream g: `win` = H + NT*T float2, linear (no wrap inside a
+		 * FIR). During epoch e = t/NT sample m sits at position m - e*NT*T + H, so the FIR
+		 * of local sample nl of tile t reads positions [(t%NT)*T + nl, ... + taps). When a
+		 * new epoch starts the last H samples are moved to the front; NT >= 2 + H/T keeps
+		 * that move clear of the FIR reads of the tile still in flight.
+		 * Prologue: history (taps-1 samples) at [0,H), tile 0 at [H, H+T).
+		 */
 		for (int i = ptid; i < Gc*(H + T); i += 32*P) {
 			const int g = i/(H + T), j = i - g*(H + T);
 			const int sid = a.first_stream + g0 + g;
@@ -259,19 +326,21 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 				const int m = j - H;
 				v = (m < a.nsamples) ? ingest(a.raw + (size_t)(g0 + g)*a.raw_stride, c.bps, m) : make_float2(0.f, 0.f);
 			}
-			rings[(size_t)g*ring + (j & mask)] = v;
+			wins[(size_t)g*win + j] = v;
 		}
 		producers_sync();
 
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
+			const int te = t % NT;                                      /* tile within the epoch */
+			const bool more = t + 1 < ntiles;
 			/* 1. prefetch this warp's share of tile t+1 (registers) */
 			float2 nxt[MAXU];
 #pragma unroll
 			for (int m = 0; m < MAXU; m++) {
 				const int u = pw + P*m;
 				nxt[m] = make_float2(0.f, 0.f);
-				if (u < units) {
+				if (more && u < units) {
 					const int g = u/SLABS, sl = u - g*SLABS;
 					const int n = (t + 1)*T + sl*32 + lane;
 					if (n < a.nsamples) nxt[m] = ingest(a.raw + (size_t)(g0 + g)*a.raw_stride, c.bps, n);
@@ -282,31 +351,39 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 #pragma unroll 1
 			for (int u = pw; u < units; u += P) {
 				const int g = u/SLABS, sl = u - g*SLABS;
-				const int nl = sl*32 + lane;                        /* sample within tile */
-				fir_all_phases<L>(rings + (size_t)g*ring, mask, t*T + nl, hT, taps,
+				const int nl = sl*32 + lane;                            /* sample within tile */
+				fir_all_phases<L>(wins + (size_t)g*win + te*T + nl, hT, taps,
 				                  tiles + ((size_t)g*S + slot)*T*L + nl*L);
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&full[slot]);
-			/* 3. append tile t+1 to the delay lines */
+			/* 3. append tile t+1 to the delay lines (new epoch: move the last H samples first) */
+			if (more) {
+				const bool wrap = (te + 1 == NT);
 #pragma unroll
-			for (int m = 0; m < MAXU; m++) {
-				const int u = pw + P*m;
-				if (u < units) {
-					const int g = u/SLABS, sl = u - g*SLABS;
-					const int n = (t + 1)*T + sl*32 + lane;
-					rings[(size_t)g*ring + ((n + H) & mask)] = nxt[m];
+				for (int m = 0; m < MAXU; m++) {
+					const int u = pw + P*m;
+					if (u < units) {
+						const int g = u/SLABS, sl = u - g*SLABS;
+						float2 *w = wins + (size_t)g*win;
+						if (wrap && sl == 0)
+							for (int j = lane; j < H; j += 32) w[j] = w[NT*T + j];
+						const int base = wrap ? H : (te + 1)*T + H;
+						w[base + sl*32 + lane] = nxt[m];
+					}
 				}
 			}
 			producers_sync();
 		}
 
-		/* epilogue: the last taps-1 samples become the next call's delay line */
+		/* epilogue: the last taps-1 samples become the next call's delay line. The window still
+		 * has the layout of the last tile's epoch (step 3 is skipped after the last tile). */
+		const int e_last = (ntiles - 1)/NT;
 		for (int i = ptid; i < Gc*H; i += 32*P) {
 			const int g = i/H, j = i - g*H;
 			const int sid = a.first_stream + g0 + g;
-			const int m = a.nsamples - H + j;                       /* may be negative: old history */
-			a.hist[(size_t)sid*H + j] = rings[(size_t)g*ring + ((m + H) & mask)];
+			const int m = a.nsamples - H + j;                           /* may be negative: old history */
+			a.hist[(size_t)sid*H + j] = wins[(size_t)g*win + (m - e_last*NT*T + H)];
 		}
 	}
 }
@@ -314,7 +391,8 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 /* ------------------------------------------------------------- host side --- */
 
 static int g_num_sms = 0;
-static int g_max_smem = 0;
+static int g_max_smem = 0;       /* opt-in per block */
+static int g_sm_smem = 0;        /* per SM */
 
 static size_t ws_fixed_smem(int taps, int L)
 {
@@ -322,16 +400,12 @@ static size_t ws_fixed_smem(int taps, int L)
 	return 2*WS_SLOTS*sizeof(uint64_t) + 32*sizeof(float) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
 }
 
-static int ws_ring(int taps)
-{
-	int need = (taps - 1) + 2*WS_T, r = 64;
-	while (r < need) r <<= 1;
-	return r;
-}
+static int ws_nt(int taps) { return 2 + (taps - 1 + WS_T - 1)/WS_T; }
+static int ws_win(int taps) { return (taps - 1) + ws_nt(taps)*WS_T; }
 
 static size_t ws_stream_smem(int taps, int L)
 {
-	return (size_t)ws_ring(taps)*sizeof(float2) + (size_t)WS_SLOTS*WS_T*L*sizeof(float2);
+	return (size_t)ws_win(taps)*sizeof(float2) + (size_t)WS_SLOTS*WS_T*L*sizeof(float2);
 }
 
 bool ws_supported(const lrpt_consts_t &c)
@@ -339,9 +413,18 @@ bool ws_supported(const lrpt_consts_t &c)
 	return c.interp >= 1 && c.interp <= WS_MAX_L && c.taps >= 1 && c.taps <= WS_MAX_TAPS;
 }
 
+template <int L, bool OQ> static cudaError_t ws_set_attr1()
+{
+	cudaError_t e = cudaFuncSetAttribute(demod_ws_kernel<L, OQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+	if (e) return e;
+	return cudaFuncSetAttribute(demod_ws_kernel<L, OQ>, cudaFuncAttributePreferredSharedMemoryCarveout,
+	                            cudaSharedmemCarveoutMaxShared);
+}
+
 template <int L> static cudaError_t ws_set_attr()
 {
-	return cudaFuncSetAttribute(demod_ws_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+	cudaError_t e = ws_set_attr1<L, false>();
+	return e ? e : ws_set_attr1<L, true>();
 }
 
 cudaError_t ws_prepare(int device)
@@ -349,6 +432,7 @@ cudaError_t ws_prepare(int device)
 	cudaError_t e;
 	if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, device))) return e;
 	if ((e = cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device))) return e;
+	if ((e = cudaDeviceGetAttribute(&g_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device))) return e;
 	if ((e = ws_set_attr<1>()) || (e = ws_set_attr<2>()) || (e = ws_set_attr<3>()) || (e = ws_set_attr<4>()) ||
 	    (e = ws_set_attr<5>()) || (e = ws_set_attr<6>()) || (e = ws_set_attr<7>()) || (e = ws_set_attr<8>())) return e;
 	return cudaSuccess;
@@ -356,7 +440,19 @@ cudaError_t ws_prepare(int device)
 
 template <int L> static void ws_launch_one(const lrpt_consts_t &c, const WsArgs &w, int blocks, size_t smem, cudaStream_t st)
 {
-	demod_ws_kernel<L><<<blocks, WS_THREADS, smem, st>>>(c, w);
+	if (c.oqpsk) demod_ws_kernel<L, true><<<blocks, WS_THREADS, smem, st>>>(c, w);
+	else         demod_ws_kernel<L, false><<<blocks, WS_THREADS, smem, st>>>(c, w);
+}
+
+/* Streams per CTA: spread the batch over every SM with up to WS_CTAS_PER_SM co-resident
+ * CTAs (each brings one recurrence warp and WS_PRODUCERS FIR warps), within shared memory. */
+static int ws_pick_g(int nstreams, size_t fixed, size_t per)
+{
+	int gfit = (int)(((size_t)g_max_smem - fixed)/per);
+	if (gfit < 1) return 0;
+	gfit = std::min(gfit, WS_MAX_G);
+	int G = (nstreams + g_num_sms*WS_CTAS_PER_SM - 1)/(g_num_sms*WS_CTAS_PER_SM);
+	return std::max(1, std::min(G, gfit));
 }
 
 cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches)
@@ -364,25 +460,23 @@ cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches)
 	const lrpt_consts_t &c = *a.c;
 	const int L = c.interp, taps = c.taps;
 	const size_t fixed = ws_fixed_smem(taps, L), per = ws_stream_smem(taps, L);
-	int gfit = (int)(((size_t)g_max_smem - fixed)/per);
-	if (gfit < 1) return cudaErrorInvalidConfiguration;
-	gfit = std::min(gfit, WS_MAX_G);
+	const int G = ws_pick_g(a.nstreams, fixed, per);
+	if (G < 1) return cudaErrorInvalidConfiguration;
 	int n = 0;
-	/* long blocks are cut so that sub-step indices stay in int32; state carries over */
+	/* long blocks are cut so that sub-step indices stay in int32; state and cursors carry over */
 	size_t done = 0;
-	uint32_t *cursor = a.d_out_off;
-	do {
+	while (done < a.nsamples) {
 		const size_t ns = std::min(a.nsamples - done, (size_t)WS_MAX_SAMPLES);
-		int G = (a.nstreams + g_num_sms - 1)/g_num_sms;             /* spread streams over all SMs */
-		G = std::max(1, std::min(G, gfit));
+		if (done && !a.d_out_off) return cudaErrorInvalidValue;     /* appending needs a cursor */
 		const int blocks = (a.nstreams + G - 1)/G;
 		WsArgs w;
 		w.taps = a.d_taps; w.states = a.d_states; w.hist = a.d_hist;
 		w.raw = reinterpret_cast<const uint8_t *>(a.d_raw) + done*(size_t)(c.bps/4); w.raw_stride = a.raw_stride;
 		w.nsamples = (int)ns;
 		w.soft = a.d_soft; w.soft_stride = a.soft_stride; w.symf = a.d_symf; w.symf_stride = a.symf_stride;
-		w.cap = a.cap; w.nsym_out = a.d_nsym; w.out_off = cursor;
-		w.first_stream = a.first_stream; w.nstreams = a.nstreams; w.G = G; w.ring = ws_ring(taps);
+		w.cap = a.cap; w.nsym_out = a.d_nsym; w.out_off = a.d_out_off;
+		w.first_stream = a.first_stream; w.nstreams = a.nstreams; w.G = G;
+		w.win = ws_win(taps); w.NT = ws_nt(taps);
 		const size_t smem = fixed + per*(size_t)G;
 		switch (L) {
 			case 1: ws_launch_one<1>(c, w, blocks, smem, st); break;
@@ -399,7 +493,7 @@ cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches)
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { if (launches) *launches = n; return e; }
 		done += ns;
-	} while (done < a.nsamples);
+	}
 	if (launches) *launches = n;
 	return cudaSuccess;
 }

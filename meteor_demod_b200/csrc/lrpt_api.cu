@@ -32,6 +32,7 @@ struct lrpt_demod {
 	uint32_t     *d_nsym   = nullptr;   /* [nstreams] last launch */
 	uint32_t     *d_off    = nullptr;   /* [nstreams] append cursors (host-buffer path) */
 	uint32_t     *h_counts = nullptr;   /* pinned [nstreams] */
+	lrpt_state_t *d_init   = nullptr;   /* [nstreams] power-on states, source of resets */
 	lrpt_state_t *h_state  = nullptr;   /* pinned scratch, one state */
 	cudaStream_t  stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t   ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -77,14 +78,22 @@ extern "C" const char *lrpt_strerror(int code)
 
 extern "C" const char *lrpt_last_error(const lrpt_demod_t *h) { return h ? h->err : "null handle"; }
 
+static int reset_on(lrpt_demod *h, cudaStream_t st)
+{
+	CU(h, cudaMemcpyAsync(h->d_states, h->d_init, sizeof(lrpt_state_t)*(size_t)h->p.nstreams,
+	                      cudaMemcpyDeviceToDevice, st));
+	if (h->H > 0)
+		CU(h, cudaMemsetAsync(h->d_hist, 0, sizeof(float2)*(size_t)h->H*h->p.nstreams, st));   /* calloc, filter.c:16 */
+	CU(h, cudaMemsetAsync(h->d_nsym, 0, sizeof(uint32_t)*h->p.nstreams, st));
+	return LRPT_OK;
+}
+
 static int upload_initial_state(lrpt_demod *h)
 {
 	std::vector<lrpt_state_t> init((size_t)h->p.nstreams, h->s0);
-	CU(h, cudaMemcpyAsync(h->d_states, init.data(), sizeof(lrpt_state_t)*init.size(),
-	                      cudaMemcpyHostToDevice, h->stream));
-	if (h->H > 0)
-		CU(h, cudaMemsetAsync(h->d_hist, 0, sizeof(float2)*(size_t)h->H*h->p.nstreams, h->stream));   /* calloc, filter.c:16 */
-	CU(h, cudaMemsetAsync(h->d_nsym, 0, sizeof(uint32_t)*h->p.nstreams, h->stream));
+	CU(h, cudaMemcpy(h->d_init, init.data(), sizeof(lrpt_state_t)*init.size(), cudaMemcpyHostToDevice));
+	int rc = reset_on(h, h->stream);
+	if (rc) return rc;
 	CU(h, cudaStreamSynchronize(h->stream));
 	memset(h->h_counts, 0, sizeof(uint32_t)*h->p.nstreams);
 	return LRPT_OK;
@@ -124,6 +133,7 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 	}
 	CUC(cudaMalloc(&h->d_taps, sizeof(float)*h->taps.size()));
 	CUC(cudaMalloc(&h->d_states, sizeof(lrpt_state_t)*p->nstreams));
+	CUC(cudaMalloc(&h->d_init, sizeof(lrpt_state_t)*p->nstreams));
 	CUC(cudaMalloc(&h->d_hist, sizeof(float2)*(size_t)(h->H > 0 ? h->H : 1)*p->nstreams));
 	CUC(cudaMalloc(&h->d_nsym, sizeof(uint32_t)*p->nstreams));
 	CUC(cudaMalloc(&h->d_off, sizeof(uint32_t)*p->nstreams));
@@ -152,7 +162,7 @@ extern "C" void lrpt_destroy(lrpt_demod_t *h)
 	cudaSetDevice(h->p.device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off);
+	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_init); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off);
 	cudaFree(h->d_raw[0]); cudaFree(h->d_raw[1]); cudaFree(h->d_soft); cudaFree(h->d_symf);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	if (h->h_state) cudaFreeHost(h->h_state);
@@ -169,7 +179,18 @@ extern "C" int lrpt_reset(lrpt_demod_t *h)
 {
 	if (!h) return LRPT_ERR_ARG;
 	CU(h, cudaSetDevice(h->p.device));
-	return upload_initial_state(h);
+	CU(h, cudaDeviceSynchronize());          /* nothing of this handle may still be in flight */
+	int rc = reset_on(h, h->stream);
+	if (rc) return rc;
+	CU(h, cudaStreamSynchronize(h->stream));
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_reset_async(lrpt_demod_t *h, void *cuda_stream)
+{
+	if (!h) return LRPT_ERR_ARG;
+	CU(h, cudaSetDevice(h->p.device));
+	return reset_on(h, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
 }
 
 /* ------------------------------------------------------------------ launch -- */

@@ -90,8 +90,14 @@ class Demod:
             raise LrptError(rc, what + ": " + self.lib.lrpt_last_error(self.h).decode())
         return rc
 
-    def reset(self):
-        self._check(self.lib.lrpt_reset(self.h), "reset")
+    def reset(self, stream=None, asynchronous=False):
+        """Back to power-on state. asynchronous=True enqueues on `stream` (torch.cuda.Stream or None =
+        the handle's stream) without synchronising the host."""
+        if asynchronous or stream is not None:
+            st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+            self._check(self.lib.lrpt_reset_async(self.h, st), "reset_async")
+        else:
+            self._check(self.lib.lrpt_reset(self.h), "reset")
 
     def capacity(self, nsamples):
         return symbol_capacity(nsamples, self.p.samplerate, self.p.symrate)

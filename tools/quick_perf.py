@@ -13,7 +13,7 @@ def run(B, N, kernel="ws", order=32, L=5, oqpsk=0, symrate=72000, bps=16, reps=3
     ts = []
     with torch.cuda.stream(st):
         for r in range(reps):
-            d.reset()
+            d.reset(stream=st)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st); d.process_device(raw, soft, stream=st); e1.record(st); st.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -27,10 +27,8 @@ if __name__ == "__main__":
     t = time.time()
     per = synth.baseband(230000, periodic=True).astype(np.complex64)
     print("period gen %.1fs" % (time.time()-t), flush=True)
-    for B, N in ((1, 1<<20), (8, 1<<20), (148, 1<<20), (592, 1<<19), (1184, 1<<19), (2368, 1<<18), (4736, 1<<18)):
+    for B, N in ((1, 1<<19), (148, 1<<19), (1024, 1<<19), (2048, 1<<19), (4736, 1<<18), (9472, 1<<17)):
         run(B, N, "ws", period=per)
-    run(148, 1<<16, "simple", period=per)
-    run(1024, 1<<16, "simple", period=per)
-    run(592, 1<<19, "ws", order=64, L=8, period=per)
+    run(4736, 1<<17, "ws", order=64, L=8, period=per)
     per80 = synth.baseband(230000, symrate=80000, oqpsk=True, periodic=True).astype(np.complex64)
-    run(592, 1<<19, "ws", oqpsk=1, symrate=80000, bps=8, period=per80)
+    run(4736, 1<<17, "ws", oqpsk=1, symrate=80000, bps=8, period=per80)
