@@ -79,6 +79,22 @@ LRPT_DEV void mbar_wait(uint64_t *bar, unsigned parity)
 		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+/* Producers wait here for the recurrence warp most of the time; back off between polls so
+ * their polling does not take issue slots away from that warp, which is the critical path. */
+LRPT_DEV void mbar_wait_relaxed(uint64_t *bar, unsigned parity)
+{
+	unsigned done;
+	for (;;) {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (done) break;
+		__nanosleep(200);
+	}
+}
+
 LRPT_DEV void producers_sync()
 {
 	asm volatile("bar.sync 1, %0;" :: "n"(32*WS_PRODUCERS) : "memory");
@@ -260,34 +276,39 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
 			mbar_wait(&full[slot], (unsigned)(t/S) & 1u);
-			if (active) {
+			{
 				const int q0 = t*T*L;
 				const int q1 = min((t + 1)*T, a.nsamples)*L;
 				const float2 *tile = my_tiles + slot*T*L;
+				/* Warp-uniform rounds, so that the lanes (streams) stay converged: in each round
+				 * every lane that still owes this tile a crossing runs its NCO search, then every
+				 * lane holding a crossing inside the tile takes its symbol step, all together. */
 				while (true) {
-					/* all lanes first run their timing NCO to the next crossing ... */
-					if (!have_x) {
-						if (Q >= q1) break;
+					if (active && !have_x && Q < q1)
 						have_x = nco_to_crossing(r, c, Q, q1, Qend, Qx, half, guess);
-					}
-					if (!have_x || Qx >= q1) break;                  /* nothing left in this tile */
-					/* ... then take the symbol step together (demod.c:35-43 / :66-83) */
-					const float2 y = tile[Qx - q0];                  /* filter_get(flt, i) */
-					const Loop saved = r;
-					float ore, oim; bool emitted;
-					if (!symbol_fast<OQ>(r, c, lut, half, y.x, y.y, ore, oim, emitted)) {
-						r = saved;                                   /* a shortcut was not provably exact */
-						emitted = symbol_event(r, c, lut, half, y.x, y.y, ore, oim);
-					}
-					if (emitted) {
-						if (r.locked_once && first_lock < 0) first_lock = nsymbols;
-						if (off + nsym < a.cap) {
-							out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
-							if (outf) outf[off + nsym] = make_float2(ore, oim);
+					__syncwarp();
+					const bool ready = active && have_x && Qx < q1;
+					if (!__any_sync(0xffffffffu, ready)) break;
+					if (ready) {
+						/* the symbol step (demod.c:35-43 / :66-83) */
+						const float2 y = tile[Qx - q0];              /* filter_get(flt, i) */
+						const Loop saved = r;
+						float ore, oim; bool emitted;
+						if (!symbol_fast<OQ>(r, c, lut, half, y.x, y.y, ore, oim, emitted)) {
+							r = saved;                               /* a shortcut was not provably exact */
+							emitted = symbol_event(r, c, lut, half, y.x, y.y, ore, oim);
 						}
-						nsym++; nsymbols++;
+						if (emitted) {
+							if (r.locked_once && first_lock < 0) first_lock = nsymbols;
+							if (off + nsym < a.cap) {
+								out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
+								if (outf) outf[off + nsym] = make_float2(ore, oim);
+							}
+							nsym++; nsymbols++;
+						}
+						have_x = false;
 					}
-					have_x = false;
+					__syncwarp();
 				}
 			}
 			__syncwarp();
@@ -347,7 +368,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 				}
 			}
 			/* 2. wait until the consumer has released this slot, then fill it */
-			if (t >= S) mbar_wait(&empty[slot], (unsigned)(t/S - 1) & 1u);
+			if (t >= S) mbar_wait_relaxed(&empty[slot], (unsigned)(t/S - 1) & 1u);
 #pragma unroll 1
 			for (int u = pw; u < units; u += P) {
 				const int g = u/SLABS, sl = u - g*SLABS;
