@@ -27,8 +27,9 @@ namespace lrpt {
 
 constexpr int WS_T        = 32;    /* samples per tile = one FIR unit per stream  */
 constexpr int WS_SLOTS    = 2;     /* FIR tile ring depth                        */
-constexpr int WS_PRODUCERS = 16;   /* producer warps                             */
-constexpr int WS_THREADS  = 32*(1 + WS_PRODUCERS);
+constexpr int WS_WARPS    = 16;    /* warps per CTA                              */
+constexpr int WS_PRODUCERS = 12;   /* FIR warps: the ones NOT on SM sub-partition 0 (warp id % 4 != 0)       */
+constexpr int WS_THREADS  = 32*WS_WARPS;
 constexpr int WS_MAX_G    = 32;    /* streams per CTA = consumer lanes           */
 constexpr int WS_CTAS_PER_SM = 1;  /* one big CTA per SM: the recurrence warp's time per symbol does not
                                       depend on how many of its 32 lanes carry a stream, so lanes are filled first */
@@ -251,6 +252,13 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 	}
 	__syncthreads();
 
+	/*
+	 * Warp roles. Warps map to the four SM sub-partitions (schedulers) by warp id % 4. The recurrence
+	 * warp (warp 0) is the critical path and latency-bound, so it gets sub-partition 0 to itself:
+	 * warps 4, 8, 12 retire at once and the twelve FIR warps fill sub-partitions 1-3, where they
+	 * are issue-bound without slowing the recurrence down.
+	 */
+	if (warp != 0 && (warp & 3) == 0) return;
 	if (warp == 0) {
 		/* ===================== consumer: one lane per stream ===================== */
 		const bool active = lane < Gc;
@@ -324,8 +332,8 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		}
 	} else {
 		/* ===================== producers: ingest + all-phase FIR ===================== */
-		const int pw = warp - 1;                                    /* 0..P-1 */
-		const int ptid = threadIdx.x - 32;
+		const int pw = (warp >> 2)*3 + (warp & 3) - 1;              /* 0..P-1 */
+		const int ptid = pw*32 + lane;
 		constexpr int SLABS = T/32;
 		const int units = Gc*SLABS;                                 /* (stream, 32-sample slab) per tile */
 		constexpr int MAXU = (WS_MAX_G*SLABS + P - 1)/P;

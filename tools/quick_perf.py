@@ -27,8 +27,11 @@ if __name__ == "__main__":
     t = time.time()
     per = synth.baseband(230000, periodic=True).astype(np.complex64)
     print("period gen %.1fs" % (time.time()-t), flush=True)
-    for B, N in ((1, 1<<19), (148, 1<<19), (1024, 1<<19), (2048, 1<<19), (4736, 1<<18), (9472, 1<<17)):
+    import sys as _s
+    cfgs = ((1, 1<<18), (2048, 1<<18), (4736, 1<<18))
+    for B, N in cfgs:
         run(B, N, "ws", period=per)
-    run(4736, 1<<17, "ws", order=64, L=8, period=per)
-    per80 = synth.baseband(230000, symrate=80000, oqpsk=True, periodic=True).astype(np.complex64)
-    run(4736, 1<<17, "ws", oqpsk=1, symrate=80000, bps=8, period=per80)
+    if "--all" in _s.argv:
+        run(4736, 1<<17, "ws", order=64, L=8, period=per)
+        per80 = synth.baseband(230000, symrate=80000, oqpsk=True, periodic=True).astype(np.complex64)
+        run(4736, 1<<17, "ws", oqpsk=1, symrate=80000, bps=8, period=per80)
