@@ -263,11 +263,13 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     with Clocks(local) as clk:
         barrier()
+        torch.cuda.nvtx.range_push("bench_timed")           # ncu --nvtx --nvtx-include "bench_timed/"
         ev[0].record(st)
         for i in range(a.steps):
             step()
             ev[i + 1].record(st)
         st.synchronize()
+        torch.cuda.nvtx.range_pop()
         barrier()
     launches = d.launch_count() - l0
     total_ms = ev[0].elapsed_time(ev[-1])
@@ -306,11 +308,13 @@ def main():
         for _ in range(max(1, min(a.warmup, 2))):
             e2e_step()
         barrier()
+        torch.cuda.nvtx.range_push("bench_e2e")
         t0 = time.perf_counter()
         for _ in range(a.steps):
             e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        torch.cuda.nvtx.range_pop()
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -335,9 +339,10 @@ def main():
     kern_ms = float(np.mean(step_ms))
     alg_bytes = B * N * (bps // 4) + 2.0 * float(counts.sum())          # raw read + soft symbols written, per launch
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None                                          # dram bytes per launch from the committed ncu capture
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(a.workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[a.workload]
+        traffic = float(tj["bytes_per_stream_sample"]) * B * N
     except Exception:
         pass
     fir_flops = B * N * 4.0 * (2 * order + 1) * interp                   # all-phase FIR, mul and add counted separately

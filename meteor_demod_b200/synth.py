@@ -128,12 +128,13 @@ def wav_header(data_bytes, fs=230000, bps=16, channels=2):
 
 
 def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 72000, seed=7,
-                   esn0_db=12.0, rms=6000.0, device="cuda", out=None):
+                   esn0_db=12.0, rms=6000.0, device="cuda", out=None, group=64):
     """Build `nstreams` distinct raw streams on the device from one tileable baseband period.
 
     Stream b = period rolled by a per-stream shift, tiled to nsamples, mixed with a per-stream
     carrier (multiple of fs/len(period) so tiling stays seamless), own phase, amplitude and noise.
-    Returns a torch tensor [nstreams, 2*nsamples] of the raw dtype. Plumbing only (torch ops).
+    Returns a torch tensor [nstreams, 2*nsamples] of the raw dtype. Plumbing only (torch ops,
+    `group` streams per batch of ops).
     """
     import torch
 
@@ -146,25 +147,29 @@ def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 7
     g.manual_seed(seed)
     rs = np.random.Generator(np.random.PCG64(seed))
     step = fs / P
-    n = torch.arange(nsamples, device=device, dtype=torch.float64)
+    kmax = int(1500 / step)
+    shift = torch.from_numpy(rs.integers(0, P, nstreams)).to(device)
+    cfo = torch.from_numpy(step * rs.integers(-kmax, kmax + 1, nstreams).astype(np.float64)).to(device)
+    ph = torch.from_numpy(rs.uniform(0, 2 * np.pi, nstreams)).to(device)
+    amp = torch.from_numpy(rs.uniform(0.6, 1.2, nstreams).astype(np.float32)).to(device)
+    n = torch.arange(nsamples, device=device)
     sigma = float(np.sqrt(sps / (10 ** (esn0_db / 10)) / 2)) if esn0_db is not None else 0.0
-    for b in range(nstreams):
-        shift = int(rs.integers(0, P))
-        cfo = step * int(rs.integers(-int(1500 / step), int(1500 / step) + 1))
-        ph = float(rs.uniform(0, 2 * np.pi))
-        amp = float(rs.uniform(0.6, 1.2))
-        idx = (torch.arange(nsamples, device=device) + shift) % P
-        z = base[idx]
-        rot = torch.exp(1j * (2 * np.pi * cfo / fs * n + ph)).to(torch.complex64)
-        y = z * rot
+    dc = torch.tensor([30.0, -20.0], device=device)
+    for b0 in range(0, nstreams, group):
+        b1 = min(nstreams, b0 + group)
+        idx = (n[None, :] + shift[b0:b1, None]) % P
+        # carrier phase reduced mod 2*pi in float64 before going to float32
+        arg = torch.remainder(2 * np.pi / fs * cfo[b0:b1, None] * n[None, :].to(torch.float64) + ph[b0:b1, None],
+                              2 * np.pi).to(torch.float32)
+        y = base[idx] * torch.polar(torch.ones_like(arg), arg)
         if sigma:
-            y = y + sigma * torch.complex(torch.randn(nsamples, device=device, generator=g),
-                                          torch.randn(nsamples, device=device, generator=g))
+            y = y + sigma * torch.complex(torch.randn(y.shape, device=device, generator=g),
+                                          torch.randn(y.shape, device=device, generator=g))
+        v = torch.view_as_real(y)
         if bps == 8:
-            v = torch.view_as_real(y * (64.0 / 3.0 * amp)).round() + 128
-            out[b] = v.clamp(0, 255).reshape(-1).to(dt)
+            v = (v * (64.0 / 3.0 * amp[b0:b1, None, None])).round() + 128
+            out[b0:b1] = v.clamp(0, 255).reshape(b1 - b0, -1).to(dt)
         else:
-            v = torch.view_as_real(y * (rms * amp))
-            v = (v + torch.tensor([30.0, -20.0], device=device)).round().clamp(-32768, 32767)
-            out[b] = v.reshape(-1).to(dt)
+            v = ((v * (rms * amp[b0:b1, None, None])) + dc).round().clamp(-32768, 32767)
+            out[b0:b1] = v.reshape(b1 - b0, -1).to(dt)
     return out
