@@ -1,0 +1,289 @@
+/*
+ * lrpt_demod -- C host with the reference's command line (meteor_demod main.c) in front
+ * of the B200 demodulator (liblrpt_b200.so, include/lrpt_b200.h).
+ *
+ * What is kept from the reference, because it decides WHICH bytes come out:
+ *   - flags and defaults                         main.c:19,35-51,66-79,82-134
+ *   - -d Hz -> rad/symbol                        main.c:136
+ *   - --stdout implies -B -q; "-" is stdin       main.c:145-148,155-157
+ *   - canonical 44-byte WAV header; its sample rate / bits override -s / --bps; rewind on
+ *     failure (which silently fails on a pipe)   wavfile.c:34-49, main.c:164-165
+ *   - numbers are parsed like human_to_float: k/M suffix, truncated to an integer
+ *                                                utils.c:62-85
+ *   - only whole 32 KiB input blocks are used    wavfile.c:55
+ *   - soft symbols leave in 512-symbol blocks, a block only if the PLL had locked once
+ *     when it completed; the last partial block always   main.c:308-323
+ *   - status line text                           main.c:253-258
+ * What is not: the ncurses TUI (always batch-style status), the per-sample demod calls
+ * (one lrpt_process call per input slab instead), and the final-flush length bug
+ * (main.c:321 writes 2*ring_idx bytes, the second half stale or out of bounds) unless
+ * --ref-compatible-tail asks for the reference's byte count.
+ */
+#include <getopt.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "lrpt_b200.h"
+
+#define SHORTOPTS "a:Bb:d:f:hm:o:O:qR:r:s:S:v"
+#define RINGSIZE 512                      /* symbols, main.c:20 */
+#define FILE_BLOCK 32768                  /* wavfile.c:8 */
+#define SLAB_BLOCKS 512                   /* 16 MiB of input per lrpt_process call */
+
+#ifndef VERSION
+#define VERSION "1.0-b200"
+#endif
+
+enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL };
+
+static struct option longopts[] = {
+	{ "batch",        0, NULL, 'B' }, { "pll-bw",       1, NULL, 'b' },
+	{ "freq-delta",   1, NULL, 'd' }, { "fir-order",    1, NULL, 'f' },
+	{ "help",         0, NULL, 'h' }, { "mode",         1, NULL, 'm' },
+	{ "output",       1, NULL, 'o' }, { "oversamp",     1, NULL, 'O' },
+	{ "quiet",        0, NULL, 'q' }, { "refresh-rate", 1, NULL, 'R' },
+	{ "symrate",      1, NULL, 'r' }, { "stdout",       0, NULL, OPT_STDOUT },
+	{ "samplerate",   1, NULL, 's' }, { "bps",          1, NULL, 'S' },
+	{ "version",      0, NULL, 'v' }, { "device",       1, NULL, OPT_DEVICE },
+	{ "ref-compatible-tail", 0, NULL, OPT_REFTAIL },
+	{ NULL, 0, NULL, 0 }
+};
+
+static void
+usage(const char *pname)
+{
+	fprintf(stderr, "Usage: %s [options] file_in\n", pname);
+	fprintf(stderr,
+	        "   -B, --batch             Script-friendly status output (no control characters)\n"
+	        "   -m, --mode <mode>       Modulation scheme (default: qpsk, valid modes: qpsk, oqpsk)\n"
+	        "   -o, --output <file>     Output decoded symbols to <file>\n"
+	        "   -q, --quiet             Do not print status information\n"
+	        "   -r, --symrate <rate>    Set the symbol rate to <rate> (default: 72000)\n"
+	        "   -R, --refresh-rate <ms> Refresh the status line every <ms> ms (default: 50ms, 2000ms in batch mode)\n"
+	        "   -s, --samplerate <samp> Force the input samplerate to <samp> (default: auto)\n"
+	        "       --bps <bps>         Force the input bits per sample to <bps> (default: 16)\n"
+	        "       --stdout            Write output symbols to stdout (implies -B, -q)\n"
+	        "       --device <n>        CUDA device ordinal (default: 0)\n"
+	        "       --ref-compatible-tail  Final flush writes the reference's byte count (main.c:321)\n"
+	        "\n"
+	        "   -h, --help              Print this help screen\n"
+	        "   -v, --version           Print version info\n"
+	        "\n"
+	        "Advanced options:\n"
+	        "   -b, --pll-bw <bw>       Set the PLL bandwidth to <bw> (default: 1)\n"
+	        "   -d, --freq-delta <freq> Set the maximum carrier deviation to <freq> (default: +-3.5kHz)\n"
+	        "   -f, --fir-order <ord>   Set the RRC filter order to <ord> (default: 32)\n"
+	        "   -O, --oversamp <mult>   Set the interpolation factor to <mult> (default: 5)\n");
+}
+
+/* utils.c:62-85: "137.1M" -> 137100000, result truncated to int before it becomes a float */
+static float
+human_to_float(const char *human)
+{
+	const char *suffix;
+	float tmp = atof(human);
+	int ret;
+	for (suffix = human; (*suffix >= '0' && *suffix <= '9') || *suffix == '.'; suffix++)
+		;
+	switch (*suffix) {
+		case 'k': case 'K': ret = tmp*1000; break;
+		case 'M': ret = tmp*1000000; break;
+		default: ret = tmp; break;
+	}
+	return ret;
+}
+
+static char *
+gen_fname(void)                               /* utils.c:8-19 */
+{
+	static char name[sizeof("LRPT_YYYY_MM_DD_HH_MM.s") + 1];
+	time_t t = time(NULL);
+	strftime(name, sizeof(name), "LRPT_%Y_%m_%d-%H_%M.s", localtime(&t));
+	return name;
+}
+
+struct wave_header {                          /* wavfile.c:16-31 */
+	char riff[4]; uint32_t chunk_size; char wave[4];
+	char fmt[4]; uint32_t subchunk_size; uint16_t audio_format, num_channels;
+	uint32_t sample_rate, byte_rate; uint16_t block_align, bits_per_sample;
+	char data[4]; uint32_t subchunk2_size;
+};
+
+static int
+wav_parse(FILE *fd, int *samplerate, int *bps)       /* wavfile.c:34-49 */
+{
+	struct wave_header h;
+	if (!fread(&h, sizeof(h), 1, fd)) return 1;
+	if (strncmp(h.riff, "RIFF", 4) || strncmp(h.wave, "WAVE", 4) || h.num_channels != 2) return 1;
+	if (!(*bps = h.bits_per_sample)) return 1;
+	*samplerate = (int)h.sample_rate;
+	return 0;
+}
+
+static double
+now_ms(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec*1e3 + ts.tv_nsec*1e-6;
+}
+
+int
+main(int argc, char *argv[])
+{
+	float pll_bw = 1, symrate = 72000.0f, freq_max_delta = -1;
+	int rrc_order = 32, interp_factor = 5, quiet = 0, oqpsk = 0, batch = 0;
+	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0;
+	char *output_fname = NULL;
+	FILE *in, *out;
+	int c;
+
+	while ((c = getopt_long(argc, argv, SHORTOPTS, longopts, NULL)) != -1) {
+		switch (c) {
+			case OPT_STDOUT: stdout_mode = 1; break;
+			case OPT_DEVICE: device = atoi(optarg); break;
+			case OPT_REFTAIL: ref_tail = 1; break;
+			case 'b': pll_bw = human_to_float(optarg); break;
+			case 'B': batch = 1; break;
+			case 'd': freq_max_delta = human_to_float(optarg); break;
+			case 'f': rrc_order = atoi(optarg); break;
+			case 'h': usage(argv[0]); return 0;
+			case 'm': if (!strcmp(optarg, "oqpsk")) oqpsk = 1; break;      /* anything else: qpsk, main.c:103-105 */
+			case 'o': output_fname = optarg; break;
+			case 'O': interp_factor = atoi(optarg); break;
+			case 'q': quiet = 1; break;
+			case 'R': update_interval = atoi(optarg); break;
+			case 'r': symrate = human_to_float(optarg); break;
+			case 's': samplerate = human_to_float(optarg); break;
+			case 'S': bps = atoi(optarg); break;
+			case 'v': fprintf(stderr, "lrpt_demod (meteor_demod compatible) v" VERSION "\n"); return 0;
+			default: usage(argv[0]); return 1;
+		}
+	}
+	freq_max_delta = lrpt_freq_delta_from_hz(freq_max_delta, symrate);           /* main.c:136 */
+	if (argc - optind < 1) { usage(argv[0]); return 1; }
+	if (!output_fname) output_fname = gen_fname();
+	if (update_interval < 0) update_interval = batch ? 2000 : 50;
+	if (stdout_mode) { batch = 1; quiet = 1; }
+
+	if (!strcmp(argv[optind], "-")) { in = stdin; batch = 1; }
+	else if (!(in = fopen(argv[optind], "rb"))) { fprintf(stderr, "Could not open input file\n"); return 1; }
+
+	if (wav_parse(in, &samplerate, &bps)) fseek(in, 0, SEEK_SET);    /* fails silently on a pipe, as in the reference */
+	if (samplerate < 0) {
+		fprintf(stderr, "Could not auto-detect sample rate. Please specify it with -s <samplerate>\n");
+		usage(argv[0]);
+		return 1;
+	}
+	if (!bps) { fprintf(stderr, "Could not auto-detect bits per sample, assuming 16\n"); bps = 16; }
+	if (bps != 8 && bps != 16 && bps != 32) { fprintf(stderr, "Unsupported bits per sample: %d\n", bps); return 1; }
+
+	if (stdout_mode) out = stdout;
+	else if (!(out = fopen(output_fname, "wb"))) { fprintf(stderr, "Could not open output file\n"); return 1; }
+
+	lrpt_params_t p;
+	memset(&p, 0, sizeof(p));
+	p.pll_bw = pll_bw; p.sym_bw = 0.00005f; p.freq_max = freq_max_delta;
+	p.samplerate = samplerate; p.symrate = (int)symrate;                     /* float -> int, main.c:187 */
+	p.interp_factor = interp_factor; p.rrc_order = rrc_order; p.oqpsk = oqpsk; p.bps = bps;
+	p.device = device; p.nstreams = 1; p.kernel = LRPT_KERNEL_AUTO;
+	lrpt_demod_t *h = NULL;
+	int rc = lrpt_create(&h, &p);
+	if (rc) { fprintf(stderr, "lrpt_create failed: %s\n", lrpt_strerror(rc)); return 1; }
+
+	unsigned long file_len = 0;
+	{
+		long pos = ftell(in);
+		if (pos >= 0 && !fseek(in, 0, SEEK_END)) { long e = ftell(in); file_len = e > 0 ? (unsigned long)e : 0; fseek(in, pos, SEEK_SET); }
+	}
+	if (!quiet) { printf("Input: %s, output: %s\n", argv[optind], output_fname); printf("Demodulator initialized\n"); }
+
+	const size_t slab_bytes = (size_t)SLAB_BLOCKS*FILE_BLOCK;
+	const size_t bytes_per_sample = (size_t)bps/4;
+	const size_t slab_samples = slab_bytes/bytes_per_sample;
+	const size_t cap = slab_samples;                       /* a symbol needs at least one sample in any sane setup */
+	uint8_t *raw = malloc(slab_bytes);
+	int8_t *soft = malloc(2*cap);
+	int8_t ring[2*RINGSIZE];                               /* the partial block carried between slabs */
+	int8_t prev_block[2*RINGSIZE];                         /* last complete block, for --ref-compatible-tail */
+	size_t ring_idx = 0;                                   /* int8 values in `ring`, as in main.c:291 */
+	unsigned long long nsym_total = 0, bytes_out = 0, bytes_in = 0;
+	long long first_lock = -1;
+	double last_status = now_ms();
+	memset(prev_block, 0, sizeof(prev_block));
+	if (!raw || !soft) { fprintf(stderr, "out of memory\n"); return 1; }
+
+	for (;;) {
+		/* whole 32 KiB blocks only: a trailing partial block is never consumed (wavfile.c:55) */
+		size_t got = 0;
+		while (got < slab_bytes) {
+			size_t r = fread(raw + got, 1, slab_bytes - got, in);
+			if (!r) break;
+			got += r;
+		}
+		const size_t use = got/FILE_BLOCK*FILE_BLOCK;
+		if (!use) break;
+		size_t nsym = 0;
+		rc = lrpt_process(h, raw, use/bytes_per_sample, soft, cap, &nsym, &first_lock);
+		if (rc) { fprintf(stderr, "lrpt_process failed: %s (%s)\n", lrpt_strerror(rc), lrpt_last_error(h)); return 1; }
+		bytes_in += use;
+
+		/* 512-symbol blocks, written iff the PLL had locked once when the block completed (main.c:308-316) */
+		size_t i = 0;
+		while (i < 2*nsym) {
+			size_t take = 2*RINGSIZE - ring_idx;
+			if (take > 2*nsym - i) take = 2*nsym - i;
+			memcpy(ring + ring_idx, soft + i, take);
+			ring_idx += take; i += take;
+			if (ring_idx == 2*RINGSIZE) {
+				const unsigned long long block_last = nsym_total + i/2 - 1;      /* index of the block's last symbol */
+				if (first_lock >= 0 && (unsigned long long)first_lock <= block_last) {
+					fwrite(ring, RINGSIZE, 2, out);
+					bytes_out += 2*RINGSIZE;
+				}
+				memcpy(prev_block, ring, sizeof(ring));
+				ring_idx = 0;
+			}
+		}
+		nsym_total += nsym;
+
+		if (!quiet && now_ms() - last_status >= update_interval) {
+			lrpt_status_t st;
+			lrpt_status(h, 0, &st);
+			const float freq_hz = st.pll_freq*symrate/(2*M_PI)*(oqpsk ? 2 : 1);          /* main.c:250 */
+			const float rate_hz = st.mm_omega*(samplerate*interp_factor)/(2*M_PI);       /* main.c:251 */
+			printf(batch ? "\n" : "\033[1K\r");
+			printf("(%5.1f%%) Carrier: %+7.1f Hz, Symbol rate: %.1f Hz, Locked: %s",
+			       file_len ? 100.0*bytes_in/file_len : 0, freq_hz, rate_hz, st.locked ? "Yes" : "No");
+			fflush(stdout);
+			last_status = now_ms();
+		}
+		if (got < slab_bytes) break;                          /* EOF */
+	}
+
+	/* final flush: not lock-gated (main.c:321) */
+	fwrite(ring, 1, ring_idx, out);
+	bytes_out += ring_idx;
+	if (ref_tail && ring_idx) {
+		/* the reference writes ring_idx more bytes: stale ring content, then (beyond the ring) out of bounds */
+		size_t k;
+		for (k = ring_idx; k < 2*ring_idx; k++) fputc(k < 2*RINGSIZE ? prev_block[k] : 0, out);
+	}
+	if (!quiet) {
+		lrpt_status_t st;
+		lrpt_status(h, 0, &st);
+		printf(batch ? "\n" : "\033[1K\r");
+		printf("(%5.1f%%) Carrier: %+7.1f Hz, Symbol rate: %.1f Hz, Locked: %s\n",
+		       file_len ? 100.0*bytes_in/file_len : 0, st.pll_freq*symrate/(2*M_PI)*(oqpsk ? 2 : 1),
+		       st.mm_omega*(samplerate*interp_factor)/(2*M_PI), st.locked ? "Yes" : "No");
+	}
+
+	lrpt_destroy(h);
+	free(raw); free(soft);
+	if (out != stdout) fclose(out);
+	if (in != stdin) fclose(in);
+	return 0;
+}

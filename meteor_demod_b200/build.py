@@ -56,7 +56,23 @@ def build(verbose=False, force=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    build_host(verbose, force)
     return SO
+
+
+HOST_SRC = os.path.join(os.path.dirname(HERE), "host", "lrpt_demod.c")
+HOST_BIN = os.path.join(os.path.dirname(HERE), "host", "lrpt_demod")
+
+
+def build_host(verbose=False, force=False):
+    """The C host (reference-compatible command line) linked against liblrpt_b200.so."""
+    if force or _stale(HOST_BIN, [HOST_SRC, SO, os.path.join(INC, "lrpt_b200.h")]):
+        cmd = [CC, "-O2", "-std=gnu99", "-Wall", "-Wextra", "-I", INC, "-o", HOST_BIN, HOST_SRC,
+               "-L", HERE, "-llrpt_b200", "-Wl,-rpath,$ORIGIN/../meteor_demod_b200", "-lm"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return HOST_BIN
 
 
 if __name__ == "__main__":
