@@ -144,6 +144,13 @@ int  lrpt_process_batch_device(lrpt_demod_t *h, const void *d_raw_iq, size_t raw
                                size_t nsamples, int8_t *d_soft, size_t soft_stride, size_t cap,
                                uint32_t *d_nsym, float *d_sym_f32, size_t symf_stride,
                                void *cuda_stream);
+/*
+ * Optional side output of lrpt_process_batch_device: for every symbol the timing sub-step that produced
+ * it (input sample index * interp_factor + sub-step, counted from the start of the call; demod.c:33-35),
+ * as uint32 at d_index + stream*stride (bytes), same capacity as the soft output. Time-shard stitching
+ * needs it. NULL switches it off again.
+ */
+int  lrpt_set_symbol_index_output(lrpt_demod_t *h, uint32_t *d_index, size_t stride);
 int  lrpt_sync(lrpt_demod_t *h, void *cuda_stream);
 /* per-stream symbol counts of the most recent call (host copy; call after lrpt_sync) */
 int  lrpt_get_counts(lrpt_demod_t *h, uint32_t *nsym, int nstreams);
@@ -156,6 +163,15 @@ int  lrpt_status(lrpt_demod_t *h, int stream, lrpt_status_t *st);
 size_t lrpt_state_size(const lrpt_demod_t *h);       /* bytes of one state blob */
 int  lrpt_export_state(lrpt_demod_t *h, int stream, void *buf, size_t *len);
 int  lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, size_t len);
+
+/*
+ * Snapshot / restore of ALL streams' states on the device (time-shard two-pass scheme, sharded.py).
+ * lrpt_restore copies the snapshot back; quarter_turns (host int32[nstreams], may be NULL) then turns
+ * every stream's Costas NCO back by that many quarter turns: p_phase -= turns*pi/2 (pll.c:16), which
+ * moves a locked QPSK loop to another of its four equivalent lock points without losing lock.
+ */
+int  lrpt_snapshot(lrpt_demod_t *h);
+int  lrpt_restore(lrpt_demod_t *h, const int32_t *quarter_turns);
 
 /* ---- introspection -------------------------------------------------------------- */
 /*

@@ -50,12 +50,15 @@ SYMBOLS = {
     "lrpt_process_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                             C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                             C.c_void_p]),
+    "lrpt_set_symbol_index_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "lrpt_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lrpt_get_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lrpt_status": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Status)]),
     "lrpt_state_size": (C.c_size_t, [C.c_void_p]),
     "lrpt_export_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]),
     "lrpt_import_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "lrpt_snapshot": (C.c_int, [C.c_void_p]),
+    "lrpt_restore": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lrpt_describe": (C.c_int, [C.POINTER(Params), C.POINTER(State), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lrpt_get_taps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lrpt_get_tanh_lut": (C.c_int, [C.c_void_p, C.c_void_p]),

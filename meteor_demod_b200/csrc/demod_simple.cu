@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(64)
 demod_simple_kernel(const lrpt_consts_t c, const float *__restrict__ h, lrpt_state_t *states,
                     float2 *hist, const uint8_t *__restrict__ raw, size_t raw_stride, long long nsamples,
                     int8_t *soft, size_t soft_stride, float *symf, size_t symf_stride,
-                    unsigned cap, uint32_t *nsym_out, uint32_t *out_off, int first_stream, int nstreams)
+                    uint32_t *symq, size_t symq_stride, unsigned cap, uint32_t *nsym_out, uint32_t *out_off, int first_stream, int nstreams)
 {
 	__shared__ float lut[32];
 	if (threadIdx.x < 32) lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
@@ -30,6 +30,7 @@ demod_simple_kernel(const lrpt_consts_t c, const float *__restrict__ h, lrpt_sta
 	float2 *hs = hist + (size_t)sid*H;
 	char2 *out = reinterpret_cast<char2 *>(soft + (size_t)local*soft_stride);
 	float2 *outf = symf ? reinterpret_cast<float2 *>(reinterpret_cast<char *>(symf) + (size_t)local*symf_stride) : nullptr;
+	uint32_t *outq = symq ? reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(symq) + (size_t)local*symq_stride) : nullptr;
 
 	Loop r;
 	loop_load(r, states[sid]);
@@ -65,6 +66,7 @@ demod_simple_kernel(const lrpt_consts_t c, const float *__restrict__ h, lrpt_sta
 				if (off + nsym < cap) {
 					out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
 					if (outf) outf[off + nsym] = make_float2(ore, oim);
+					if (outq) outq[off + nsym] = (uint32_t)(n*L + i);
 				}
 				nsym++; nsymbols++;
 			}
@@ -90,7 +92,7 @@ cudaError_t launch_simple(const LaunchArgs &a, cudaStream_t st)
 	const int blocks = (a.nstreams + threads - 1)/threads;
 	demod_simple_kernel<<<blocks, threads, 0, st>>>(*a.c, a.d_taps, a.d_states, a.d_hist,
 		reinterpret_cast<const uint8_t *>(a.d_raw), a.raw_stride, (long long)a.nsamples,
-		a.d_soft, a.soft_stride, a.d_symf, a.symf_stride, a.cap, a.d_nsym, a.d_out_off, a.first_stream, a.nstreams);
+		a.d_soft, a.soft_stride, a.d_symf, a.symf_stride, a.d_symq, a.symq_stride, a.cap, a.d_nsym, a.d_out_off, a.first_stream, a.nstreams);
 	return cudaGetLastError();
 }
 

@@ -46,6 +46,7 @@ struct WsArgs {
 	int           nsamples;
 	int8_t       *soft; size_t soft_stride;
 	float        *symf; size_t symf_stride;
+	uint32_t     *symq; size_t symq_stride; uint32_t q_base;
 	unsigned      cap;
 	uint32_t     *nsym_out, *out_off;
 	int           first_stream, nstreams;
@@ -267,7 +268,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		Loop r;
 		long long nsymbols = 0, first_lock = -1;
 		unsigned off = 0, nsym = 0;
-		char2 *out = nullptr; float2 *outf = nullptr;
+		char2 *out = nullptr; float2 *outf = nullptr; uint32_t *outq = nullptr;
 		if (active) {
 			loop_load(r, a.states[sid]);
 			nsymbols = a.states[sid].nsymbols;
@@ -275,6 +276,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 			off = a.out_off ? a.out_off[local] : 0u;
 			out = reinterpret_cast<char2 *>(a.soft + (size_t)local*a.soft_stride);
 			if (a.symf) outf = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.symf) + (size_t)local*a.symf_stride);
+			if (a.symq) outq = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.symq) + (size_t)local*a.symq_stride);
 		}
 		const int Qend = a.nsamples*L;          /* total timing sub-steps of this launch */
 		int Q = 0;                              /* sub-steps already taken               */
@@ -300,6 +302,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 					if (ready) {
 						/* the symbol step (demod.c:35-43 / :66-83) */
 						const float2 y = tile[Qx - q0];              /* filter_get(flt, i) */
+						const int Qsym = Qx;
 						const Loop saved = r;
 						float ore, oim; bool emitted;
 						if (!symbol_fast<OQ>(r, c, lut, half, y.x, y.y, ore, oim, emitted)) {
@@ -311,6 +314,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 							if (off + nsym < a.cap) {
 								out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
 								if (outf) outf[off + nsym] = make_float2(ore, oim);
+								if (outq) outq[off + nsym] = a.q_base + (uint32_t)Qsym;
 							}
 							nsym++; nsymbols++;
 						}
@@ -503,6 +507,7 @@ cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches)
 		w.raw = reinterpret_cast<const uint8_t *>(a.d_raw) + done*(size_t)(c.bps/4); w.raw_stride = a.raw_stride;
 		w.nsamples = (int)ns;
 		w.soft = a.d_soft; w.soft_stride = a.soft_stride; w.symf = a.d_symf; w.symf_stride = a.symf_stride;
+		w.symq = a.d_symq; w.symq_stride = a.symq_stride; w.q_base = (uint32_t)(done*(size_t)L);
 		w.cap = a.cap; w.nsym_out = a.d_nsym; w.out_off = a.d_out_off;
 		w.first_stream = a.first_stream; w.nstreams = a.nstreams; w.G = G;
 		w.win = ws_win(taps); w.NT = ws_nt(taps);

@@ -19,6 +19,9 @@ struct LaunchArgs {
 	size_t        soft_stride;
 	float        *d_symf;        /* optional float symbols, + s*symf_stride bytes */
 	size_t        symf_stride;
+	uint32_t     *d_symq;        /* optional: timing sub-step index (sample*interp + phase, counted from the
+	                                start of this call) of every symbol, + s*symq_stride bytes */
+	size_t        symq_stride;
 	unsigned      cap;           /* symbols per stream that fit */
 	uint32_t     *d_nsym;        /* [nstreams] symbols produced by this launch (may be NULL) */
 	uint32_t     *d_out_off;     /* [nstreams] append cursor: symbols already in d_soft; advanced by the

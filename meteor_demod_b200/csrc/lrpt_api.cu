@@ -33,6 +33,8 @@ struct lrpt_demod {
 	uint32_t     *d_off    = nullptr;   /* [nstreams] append cursors (host-buffer path) */
 	uint32_t     *h_counts = nullptr;   /* pinned [nstreams] */
 	lrpt_state_t *d_init   = nullptr;   /* [nstreams] power-on states, source of resets */
+	lrpt_state_t *d_snap   = nullptr;   /* [nstreams] lrpt_snapshot */
+	float2       *d_snap_hist = nullptr;
 	lrpt_state_t *h_state  = nullptr;   /* pinned scratch, one state */
 	cudaStream_t  stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t   ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -40,6 +42,7 @@ struct lrpt_demod {
 	void   *d_raw[2] = {nullptr, nullptr}; size_t d_raw_bytes = 0;
 	int8_t *d_soft = nullptr; size_t d_soft_bytes = 0;
 	float  *d_symf = nullptr; size_t d_symf_bytes = 0;
+	uint32_t *d_symq_user = nullptr; size_t symq_stride_user = 0;   /* optional side output, device path */
 	unsigned long long launches = 0;
 	char err[256];
 };
@@ -162,7 +165,7 @@ extern "C" void lrpt_destroy(lrpt_demod_t *h)
 	cudaSetDevice(h->p.device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_init); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off);
+	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_init); cudaFree(h->d_snap); cudaFree(h->d_snap_hist); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off);
 	cudaFree(h->d_raw[0]); cudaFree(h->d_raw[1]); cudaFree(h->d_soft); cudaFree(h->d_symf);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	if (h->h_state) cudaFreeHost(h->h_state);
@@ -226,6 +229,7 @@ extern "C" int lrpt_process_batch_device(lrpt_demod_t *h, const void *d_raw_iq, 
 	a.d_raw = d_raw_iq; a.raw_stride = raw_stride; a.nsamples = nsamples;
 	a.d_soft = d_soft; a.soft_stride = soft_stride; a.cap = (unsigned)cap;
 	a.d_symf = d_sym_f32; a.symf_stride = symf_stride;
+	a.d_symq = h->d_symq_user; a.symq_stride = h->symq_stride_user;
 	a.d_nsym = nullptr; a.d_out_off = h->d_off;              /* cursor doubles as the per-call count */
 	a.first_stream = 0; a.nstreams = h->p.nstreams;
 	CU(h, cudaMemsetAsync(h->d_off, 0, sizeof(uint32_t)*h->p.nstreams, st));
@@ -236,6 +240,13 @@ extern "C" int lrpt_process_batch_device(lrpt_demod_t *h, const void *d_raw_iq, 
 	if (d_nsym)
 		CU(h, cudaMemcpyAsync(d_nsym, h->d_off, sizeof(uint32_t)*h->p.nstreams, cudaMemcpyDeviceToDevice, st));
 	CU(h, cudaMemcpyAsync(h->h_counts, h->d_off, sizeof(uint32_t)*h->p.nstreams, cudaMemcpyDeviceToHost, st));
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_set_symbol_index_output(lrpt_demod_t *h, uint32_t *d_index, size_t stride)
+{
+	if (!h || (((uintptr_t)d_index | stride) & 3)) return LRPT_ERR_ARG;
+	h->d_symq_user = d_index; h->symq_stride_user = stride;
 	return LRPT_OK;
 }
 
@@ -420,6 +431,40 @@ extern "C" int lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, s
 	if (h->H > 0)
 		CU(h, cudaMemcpy(h->d_hist + (size_t)stream*h->H, (const char *)buf + sizeof(lrpt_state_t),
 		                 sizeof(float2)*(size_t)h->H, cudaMemcpyHostToDevice));
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_snapshot(lrpt_demod_t *h)
+{
+	if (!h) return LRPT_ERR_ARG;
+	CU(h, cudaSetDevice(h->p.device));
+	CU(h, cudaDeviceSynchronize());
+	const size_t ns = (size_t)h->p.nstreams, nh = (size_t)(h->H > 0 ? h->H : 1)*ns;
+	if (!h->d_snap) {
+		CU(h, cudaMalloc(&h->d_snap, sizeof(lrpt_state_t)*ns));
+		CU(h, cudaMalloc(&h->d_snap_hist, sizeof(float2)*nh));
+	}
+	CU(h, cudaMemcpy(h->d_snap, h->d_states, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToDevice));
+	CU(h, cudaMemcpy(h->d_snap_hist, h->d_hist, sizeof(float2)*nh, cudaMemcpyDeviceToDevice));
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_restore(lrpt_demod_t *h, const int32_t *quarter_turns)
+{
+	if (!h || !h->d_snap) return LRPT_ERR_ARG;
+	CU(h, cudaSetDevice(h->p.device));
+	CU(h, cudaDeviceSynchronize());
+	const size_t ns = (size_t)h->p.nstreams, nh = (size_t)(h->H > 0 ? h->H : 1)*ns;
+	CU(h, cudaMemcpy(h->d_hist, h->d_snap_hist, sizeof(float2)*nh, cudaMemcpyDeviceToDevice));
+	if (!quarter_turns) {
+		CU(h, cudaMemcpy(h->d_states, h->d_snap, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToDevice));
+		return LRPT_OK;
+	}
+	std::vector<lrpt_state_t> st(ns);
+	CU(h, cudaMemcpy(st.data(), h->d_snap, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToHost));
+	for (size_t s = 0; s < ns; s++)
+		st[s].p_phase = (float)((double)st[s].p_phase - (double)(quarter_turns[s] & 3)*1.57079632679489661923);
+	CU(h, cudaMemcpy(h->d_states, st.data(), sizeof(lrpt_state_t)*ns, cudaMemcpyHostToDevice));
 	return LRPT_OK;
 }
 

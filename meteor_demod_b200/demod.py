@@ -158,6 +158,16 @@ class Demod:
             symf.data_ptr() if symf is not None else None,
             symf.stride(0) * symf.element_size() if symf is not None else 0, st), "process_batch_device")
 
+    def set_symbol_index_output(self, idx=None):
+        """idx: uint32/int32 device tensor [nstreams, cap] receiving, per symbol, sample*interp + sub-step
+        (None = off). Applies to subsequent process_device calls."""
+        if idx is None:
+            self._check(self.lib.lrpt_set_symbol_index_output(self.h, None, 0), "set_symbol_index_output")
+        else:
+            self._check(self.lib.lrpt_set_symbol_index_output(self.h, idx.data_ptr(), idx.stride(0) * idx.element_size()),
+                        "set_symbol_index_output")
+        self._symq = idx
+
     def sync(self, stream=None):
         st = C.c_void_p(stream.cuda_stream) if stream is not None else None
         self._check(self.lib.lrpt_sync(self.h, st), "sync")
@@ -213,6 +223,18 @@ class Demod:
         d = state_to_dict(s)
         d["history"] = np.frombuffer(blob[C.sizeof(State):], np.float32).reshape(-1, 2).copy()
         return d
+
+    def snapshot(self):
+        self._check(self.lib.lrpt_snapshot(self.h), "snapshot")
+
+    def restore(self, quarter_turns=None):
+        """Back to the snapshot; quarter_turns (int per stream) turns each Costas NCO back by k*pi/2."""
+        if quarter_turns is None:
+            self._check(self.lib.lrpt_restore(self.h, None), "restore")
+        else:
+            t = np.ascontiguousarray(quarter_turns, np.int32)
+            assert t.size == self.nstreams
+            self._check(self.lib.lrpt_restore(self.h, t.ctypes.data), "restore")
 
     # -- introspection -------------------------------------------------------
     def taps(self):

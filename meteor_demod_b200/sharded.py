@@ -1,0 +1,340 @@
+"""Time-sharding of ONE long I/Q stream (BASELINE config 4).
+
+The recurrence of the reference is sequential and decision-chaotic (SURVEY.md finding 3): a
+chunk that does not start from the exact float state of its predecessor never re-joins the
+sequential trajectory bit for bit. What CAN be done in parallel is *statistical* parity
+("Tier-S"), and that is what this module does, on top of the exact batch engine:
+
+  1. plan     the stream is cut at B_c = W + c*C; chunk c is demodulated as an independent
+              stream over samples [c*C, c*C + W + C + V): W samples of warm-up from power-on
+              state (AGC, timing, Costas loop acquire), C samples it owns, V samples of overlap
+              into its successor. All chunks run in ONE batch launch (one recurrence lane each).
+  2. quadrant a QPSK Costas loop locks with a k*90 degree ambiguity. On the overlap
+              [B_c, B_c+V) chunks c-1 and c demodulate the same samples; the rotation k_c that
+              best maps c onto c-1, and the agreement of hard decisions under it, come from the
+              paired soft symbols.
+  3. scan     K_c = (k_1 + ... + k_c) mod 4 -- a prefix sum over chunk boundaries; across GPUs
+              the only exchange is the overlap symbols of a rank's last chunk (to the next
+              rank) and one integer per rank (all-gather), i.e. "boundary state handed rank to
+              rank and nothing else".
+  4. stitch   chunk c contributes the symbols between the cut points (placed mid-way between
+              two symbols of the predecessor so that a symbol instant near the boundary is
+              neither duplicated nor dropped), rotated by -K_c (exact on int8 pairs).
+  5. verify   every boundary reports its agreement (share of overlap symbols whose hard decisions
+              match after de-rotation); a low value flags a chunk that had not locked by its
+              boundary (warm-up too short for the carrier offset) or a cycle slip. The exact remedy
+              is a state hand-off: re-run that chunk from the state its predecessor exports at B_c
+              (lrpt_export_state / lrpt_import_state) -- sequential for the flagged chunks only.
+
+Chunk 0 starts from the true power-on state, so its symbols are bit-exact; later chunks are
+Tier-S: same symbol count and quadrant, a measured fraction epsilon of symbols off by more
+than one LSB -- comparable to the reference's own FMA-vs-strict build difference.
+
+Only host logic lives here (torch tensor ops for the index arithmetic, torch.distributed for the
+exchange). Demodulation is `GpuEngine` (liblrpt_b200.so); the tests feed `stitch` with chunks
+demodulated by the CPU oracle to check the logic without a GPU, including a 2-rank gloo run.
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+
+@dataclass
+class Plan:
+    nsamples: int      # samples in the stream
+    chunk: int         # C: samples owned per chunk
+    warm: int          # W: warm-up before the owned region
+    overlap: int       # V: overlap into the successor
+    interp: int        # L: timing sub-steps per sample
+    nchunks: int = 0
+
+    def __post_init__(self):
+        if self.chunk <= 0 or self.warm < 0 or self.overlap <= 0:
+            raise ValueError("chunk > 0, warm >= 0, overlap > 0 required")
+        self.nchunks = max(1, math.ceil((self.nsamples - self.warm) / self.chunk))
+
+    def start(self, c):            # first sample chunk c demodulates
+        return c * self.chunk
+
+    def boundary(self, c):         # B_c: first sample chunk c owns (chunk 0 owns from 0)
+        return 0 if c == 0 else self.warm + c * self.chunk
+
+    @property
+    def n_main(self):              # samples up to the successor's boundary
+        return self.warm + self.chunk
+
+    @property
+    def padded(self):              # buffer length that lets every chunk read n_main + overlap samples
+        return (self.nchunks - 1) * self.chunk + self.n_main + self.overlap
+
+
+def rotate_quarter_turns(soft, k):
+    """soft [...,2] int8 (I,Q) times j**k, exact: (I,Q) -> (-Q,I) per quarter turn."""
+    i, q = soft[..., 0], soft[..., 1]
+    k = k % 4
+    if isinstance(k, torch.Tensor):
+        k = k.reshape(k.shape + (1,) * (i.dim() - k.dim()))
+        ri = torch.where(k == 0, i, torch.where(k == 1, -q, torch.where(k == 2, -i, q)))
+        rq = torch.where(k == 0, q, torch.where(k == 1, i, torch.where(k == 2, -q, -i)))
+    else:
+        ri, rq = [(i, q), (-q, i), (-i, -q), (q, -i)][k]
+    return torch.stack((ri, rq), dim=-1)
+
+
+def _first_at_or_after(q, count, target):
+    """Per row: index of the first valid symbol with q >= target (q rows ascending; entries beyond
+    count are ignored). q [M,cap] int64, count [M], target [M] -> [M] int64."""
+    big = torch.iinfo(torch.int64).max
+    cols = torch.arange(q.shape[1], device=q.device)
+    qm = torch.where(cols[None, :] < count[:, None], q, torch.full_like(q, big))
+    return torch.searchsorted(qm, target[:, None].contiguous()).squeeze(1)
+
+
+def boundary_quadrants(soft, q, count, Bq, npairs=None):
+    """Rows are consecutive chunks. For every boundary (row c-1 | row c) at sub-step Bq[c-1], pair the
+    overlap symbols of the two rows and find the quarter-turn count k mapping row c onto row c-1.
+
+    Returns k [M-1] int64, agreement [M-1] float (share of pairs whose hard decisions match under k
+    and whose symbol instants differ by at most 2 sub-steps), cut [M-1] int64 (sub-step index that
+    separates the two rows' shares: mid-way between two symbols of row c-1)."""
+    M = soft.shape[0]
+    dev = soft.device
+    if M < 2:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return z, torch.zeros(0, device=dev), z
+    B = Bq.to(torch.int64)
+    a_q, a_s, a_n = q[:-1], soft[:-1], count[:-1]
+    b_q, b_s, b_n = q[1:], soft[1:], count[1:]
+    ia = _first_at_or_after(a_q, a_n, B)                     # first symbol of row c-1 inside the overlap
+    prev_q = torch.gather(a_q, 1, (ia - 1).clamp(min=0)[:, None]).squeeze(1)
+    next_q = torch.gather(a_q, 1, ia.clamp(max=a_q.shape[1] - 1)[:, None]).squeeze(1)
+    cut = torch.where((ia > 0) & (ia < a_n), (prev_q + next_q) // 2, B)
+    ib = _first_at_or_after(b_q, b_n, cut + 1)               # first symbol of row c after the cut
+    navail = torch.minimum(a_n - ia, b_n - ib).clamp(min=0)
+    nmin = int(navail.min().item())
+    npairs = nmin if npairs is None else min(npairs, nmin)
+    if npairs < 8:
+        return torch.zeros(M - 1, dtype=torch.int64, device=dev), torch.zeros(M - 1, device=dev), cut
+    j = torch.arange(npairs, device=dev)
+    ga, gb = ia[:, None] + j[None, :], ib[:, None] + j[None, :]
+    sa = torch.gather(a_s, 1, ga[:, :, None].expand(-1, -1, 2)).to(torch.float32)
+    sb = torch.gather(b_s, 1, gb[:, :, None].expand(-1, -1, 2)).to(torch.float32)
+    dq = (torch.gather(a_q, 1, ga) - torch.gather(b_q, 1, gb)).abs()
+    ai, aq, bi, bq = sa[..., 0], sa[..., 1], sb[..., 0], sb[..., 1]
+    # correlation of row c-1 with row c rotated by k quarter turns: (I,Q) -> (-Q,I) per turn
+    scores = torch.stack(((ai * bi + aq * bq).sum(1), (-ai * bq + aq * bi).sum(1),
+                          (-ai * bi - aq * bq).sum(1), (ai * bq - aq * bi).sum(1)), dim=1)
+    k = scores.argmax(dim=1)
+    rb = rotate_quarter_turns(sb, k)
+    same = (torch.sign(rb[..., 0]) == torch.sign(ai)) & (torch.sign(rb[..., 1]) == torch.sign(aq)) & (dq <= 2)
+    return k, same.float().mean(dim=1), cut
+
+
+def stitch(soft, q, count, plan, first_chunk=0, dist=None):
+    """Quadrant scan + concatenation of the owned symbols.
+
+    soft [M,cap,2] int8, q [M,cap] int64 ABSOLUTE sub-step index (sample*interp + sub-step from the
+    start of the stream), count [M] int64: the chunks this process demodulated, chunk indices
+    first_chunk .. first_chunk+M-1. Single process: pass all chunks. Multi-process (`dist` =
+    torch.distributed, ranks own consecutive runs of chunks in rank order): the exchange is (a) the
+    symbols around the next boundary of a rank's LAST chunk, sent to the next rank, (b) one all-gather
+    of an integer per rank -- the prefix sum of quarter turns is then local.
+
+    Returns dict: soft [n,2] int8 (this process's share, in stream order), k / agreement per interior
+    boundary, boundary_prev = (k, agreement) of the boundary to the previous rank, K_first, K_last."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    M, L, dev = soft.shape[0], plan.interp, soft.device
+    big = torch.iinfo(torch.int64).max
+    Bq = torch.tensor([plan.boundary(first_chunk + c) * L for c in range(1, M)], dtype=torch.int64, device=dev)
+    k, agree, cut = boundary_quadrants(soft, q, count, Bq)
+
+    k_prev, agree_prev, cut_prev = 0, None, None
+    if world > 1:
+        # (a) hand the neighbourhood of my last chunk's far boundary to the next rank
+        width = int(plan.overlap) + 64
+        pack = torch.zeros((width, 3), dtype=torch.int64, device=dev)
+        npack = torch.zeros(1, dtype=torch.int64, device=dev)
+        if first_chunk + M < plan.nchunks:
+            nextB = plan.boundary(first_chunk + M) * L
+            n = int(count[-1].item())
+            sel = (q[-1, :n] >= nextB - 64 * L).nonzero().squeeze(1)[:width]
+            pack[: sel.numel(), 0] = q[-1, sel]
+            pack[: sel.numel(), 1:] = soft[-1, sel].to(torch.int64)
+            npack[0] = sel.numel()
+        recv, nrecv = torch.zeros_like(pack), torch.zeros_like(npack)
+        reqs = [dist.isend(pack, rank + 1), dist.isend(npack, rank + 1)] if rank + 1 < world else []
+        if rank > 0:
+            dist.recv(recv, rank - 1)
+            dist.recv(nrecv, rank - 1)
+        for r_ in reqs:
+            r_.wait()
+        if rank > 0:
+            n = int(nrecv.item())
+            cap2 = max(n, soft.shape[1])
+            two_s = torch.zeros((2, cap2, 2), dtype=torch.int8, device=dev)
+            two_q = torch.zeros((2, cap2), dtype=torch.int64, device=dev)
+            two_s[0, :n] = recv[:n, 1:].to(torch.int8)
+            two_q[0, :n] = recv[:n, 0]
+            two_s[1, : soft.shape[1]] = soft[0]
+            two_q[1, : soft.shape[1]] = q[0]
+            two_n = torch.stack((torch.tensor(n, dtype=torch.int64, device=dev), count[0]))
+            kp, ap, cp = boundary_quadrants(two_s, two_q, two_n,
+                                            torch.tensor([plan.boundary(first_chunk) * L], device=dev))
+            k_prev, agree_prev, cut_prev = int(kp[0].item()), float(ap[0].item()), int(cp[0].item())
+
+    # (b) prefix sum of quarter turns over ranks
+    K_first = 0
+    if world > 1:
+        mine = torch.tensor([(k_prev + (int(k.sum().item()) if M > 1 else 0)) % 4], dtype=torch.int64, device=dev)
+        lst = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(lst, mine)
+        K_first = (sum(int(x.item()) for x in lst[:rank]) + k_prev) % 4
+
+    K = torch.empty(M, dtype=torch.int64, device=dev)
+    K[0] = K_first
+    if M > 1:
+        K[1:] = (K_first + torch.cumsum(k, 0)) % 4
+    lo = torch.full((M,), -1, dtype=torch.int64, device=dev)
+    hi = torch.full((M,), big, dtype=torch.int64, device=dev)
+    if cut_prev is not None:
+        lo[0] = cut_prev
+    if M > 1:
+        lo[1:] = cut
+        hi[:-1] = cut
+    if first_chunk + M < plan.nchunks:
+        # my last chunk ends where the next rank's first chunk begins: same rule, evaluated locally
+        nextB = torch.tensor([plan.boundary(first_chunk + M) * L], dtype=torch.int64, device=dev)
+        ia = _first_at_or_after(q[-1:], count[-1:], nextB)
+        pq = torch.gather(q[-1:], 1, (ia - 1).clamp(min=0)[:, None]).squeeze(1)
+        nq = torch.gather(q[-1:], 1, ia.clamp(max=q.shape[1] - 1)[:, None]).squeeze(1)
+        hi[-1] = torch.where((ia > 0) & (ia < count[-1:]), (pq + nq) // 2, nextB)[0]
+    else:
+        hi[-1] = plan.nsamples * L - 1                       # nothing from the zero padding
+    cols = torch.arange(soft.shape[1], device=dev)
+    keep = (cols[None, :] < count[:, None]) & (q > lo[:, None]) & (q <= hi[:, None])
+    out = rotate_quarter_turns(soft, K)[keep]
+    return dict(soft=out, k=k, agreement=agree, boundary_prev=(k_prev, agree_prev),
+                K_first=K_first, K_last=int(K[-1].item()))
+
+
+def split_chunks(nchunks, world, rank):
+    """Consecutive run of chunks of `rank`: [c0, c1)."""
+    per = math.ceil(nchunks / world)
+    return min(nchunks, rank * per), min(nchunks, (rank + 1) * per)
+
+
+def chunk_turns(res, M):
+    """Cumulative quarter turns K_c of the M local chunks, from a stitch() result."""
+    K = torch.empty(M, dtype=torch.int64, device=res["k"].device)
+    K[0] = res["K_first"]
+    if M > 1:
+        K[1:] = (res["K_first"] + torch.cumsum(res["k"], 0)) % 4
+    return K
+
+
+class GpuEngine:
+    """Chunks of one device-resident raw stream through liblrpt_b200.so, one recurrence lane each."""
+
+    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, **cfg):
+        from .demod import Demod
+        self.plan, self.raw, self.first = plan, raw, first_chunk
+        self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
+        self.d = Demod(nstreams=self.M, device=device, interp_factor=plan.interp, **cfg)
+        n_all = plan.n_main + plan.overlap
+        self.cap = (self.d.capacity(n_all) + 7) // 8 * 8
+        dev = raw.device
+        self.soft = torch.empty((self.M, 2 * self.cap), dtype=torch.int8, device=dev)
+        self.q = torch.empty((self.M, self.cap), dtype=torch.int32, device=dev)
+        self.nsym = torch.zeros(self.M, dtype=torch.int32, device=dev)
+        self.d.set_symbol_index_output(self.q)
+
+    def _view(self, first_sample_of_chunk0, nsamples):
+        p = self.plan
+        return torch.as_strided(self.raw, (self.M, 2 * nsamples), (2 * p.chunk, 1),
+                                storage_offset=2 * (p.start(self.first) + first_sample_of_chunk0))
+
+    def _result(self, offset):
+        p = self.plan
+        base = ((torch.arange(self.first, self.first + self.M, device=self.raw.device, dtype=torch.int64)
+                 * p.chunk + offset) * p.interp)
+        return (self.soft.view(self.M, self.cap, 2), self.q.to(torch.int64) + base[:, None],
+                self.nsym.to(torch.int64))
+
+    def run(self, stream=None):
+        """Single pass: every local chunk (warm-up + owned + overlap) in one batch launch. Returns
+        soft [M,cap,2] int8, q [M,cap] int64 absolute sub-step indices, count [M] int64 (device)."""
+        n_all = self.plan.n_main + self.plan.overlap
+        self.d.reset(stream=stream, asynchronous=True)
+        self.d.process_device(self._view(0, n_all), self.soft, nsym=self.nsym, stream=stream, nsamples=n_all)
+        return self._result(0)
+
+    def warm_up(self):
+        """Two-pass scheme, pass A: power-on -> boundary over the W warm-up samples; snapshot the states.
+        Returns the warm-up symbols of local chunk 0 (they are output only if it is the stream's chunk 0)."""
+        W = self.plan.warm
+        self.d.reset()
+        if W:
+            self.d.process_device(self._view(0, W), self.soft, nsym=self.nsym, nsamples=W)
+        self.d.sync()
+        n0 = int(self.nsym[0].item()) if W else 0
+        head = self.soft.view(self.M, self.cap, 2)[0, :n0].clone()
+        self.d.snapshot()
+        return head
+
+    def owned(self, quarter_turns=None):
+        """Pass B (quarter_turns None) / pass C: from the snapshot, demodulate owned + overlap samples."""
+        p = self.plan
+        n = p.chunk + p.overlap
+        self.d.restore(None if quarter_turns is None else quarter_turns.cpu().numpy().astype(np.int32))
+        self.d.process_device(self._view(p.warm, n), self.soft, nsym=self.nsym, nsamples=n)
+        self.d.sync()
+        return self._result(p.warm)
+
+    def close(self):
+        self.d.set_symbol_index_output(None)
+        self.d.close()
+
+
+def demod_sharded(raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
+                  interp_factor=5, two_pass=True, **cfg):
+    """One long stream, time-sharded over this process's GPU and, with `dist` (torch.distributed,
+    initialised), over ranks: rank r takes a consecutive run of chunks and reads them from ITS copy of
+    the stream (over-reading warm-up and overlap instead of communicating samples). raw: 1-D device
+    tensor of the raw dtype with at least 2*Plan.padded items (zeros after 2*nsamples).
+
+    two_pass=False: one launch; chunks keep whatever lock point they acquired and are de-rotated after
+    the fact. Chunks that locked an odd number of quarter turns away see the OTHER bit stream on the Q
+    arm, the only input of the timing detector (timing.c:65), and come out with a different timing
+    jitter: about 15 % of their symbols differ from the sequential run by more than 1 LSB.
+    two_pass=True (default): pass A warm-up -> snapshot; pass B owned+overlap -> quadrant scan; pass C
+    again from the snapshot with every Costas NCO turned back by its K_c quarter turns, so all chunks
+    run at the sequential run's lock point: eps drops to the 0.2-0.4 % of the reference's own
+    FMA-vs-strict builds, at the price of demodulating the owned samples twice.
+    Returns the stitch() dict plus plan, first_chunk, nchunks_local, launches."""
+    if cfg.get("oqpsk"):
+        raise NotImplementedError("time-sharding resolves the k*90 degree ambiguity of QPSK only")
+    plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    if plan.nchunks < world:
+        raise ValueError("fewer chunks (%d) than ranks (%d)" % (plan.nchunks, world))
+    c0, c1 = split_chunks(plan.nchunks, world, rank)
+    eng = GpuEngine(raw, plan, device=device, first_chunk=c0, nchunks=c1 - c0, **cfg)
+    if not two_pass:
+        soft, q, count = eng.run()
+        eng.d.sync()
+        res = stitch(soft, q, count, plan, first_chunk=c0, dist=dist)
+    else:
+        head = eng.warm_up()
+        scan = stitch(*eng.owned(), plan, first_chunk=c0, dist=dist)
+        K = chunk_turns(scan, c1 - c0)
+        res = stitch(*eng.owned(K), plan, first_chunk=c0, dist=dist)
+        res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
+        if c0 == 0:
+            res["soft"] = torch.cat((head, res["soft"]))
+    res.update(plan=plan, first_chunk=c0, nchunks_local=c1 - c0, launches=eng.d.launch_count())
+    eng.close()
+    return res

@@ -342,6 +342,7 @@ lrpt_oracle_process(lrpt_oracle_t *o, const void *raw, long nsamples,
 							soft[2*nsym+1] = lrpt_oracle_quantise(out_im);
 						}
 						if (sample_idx) sample_idx[nsym] = done + n;
+						if (o->substep_out) o->substep_out[nsym] = (unsigned char)i;
 						if (lock_once) lock_once[nsym] = (uint8_t)o->p_locked_once;
 					}
 					nsym++; o->nsymbols++;

@@ -42,6 +42,9 @@ typedef struct {
 
 	/* bookkeeping (main.c:291,298,312) */
 	long long nsamples, nsymbols, first_lock_symbol;
+
+	/* optional per-call side output: timing sub-step i (demod.c:33) of every stored symbol */
+	unsigned char *substep_out;
 } lrpt_oracle_t;
 
 /* mirrors demod_init (demod.c:8-15). Returns 0, or 1 on allocation failure / bad arguments. */

@@ -50,6 +50,7 @@ class _OracleStruct(C.Structure):
         ("p_locked", C.c_int), ("p_locked_once", C.c_int), ("p_updown", C.c_int),
         ("hist", C.POINTER(C.c_float)),
         ("nsamples", C.c_longlong), ("nsymbols", C.c_longlong), ("first_lock_symbol", C.c_longlong),
+        ("substep_out", C.c_void_p),
     ]
 
 
@@ -138,10 +139,21 @@ class Oracle:
         except Exception:
             pass
 
-    def process(self, raw, cap=None, want_float=True):
+    def process(self, raw, cap=None, want_float=True, want_substep=False):
+        """want_substep adds `q` = sample_idx*interp + timing sub-step (the CUDA path's symbol index output)."""
+        a = _as_raw(raw, self.bps)
+        ncap = (a.size // 2 + 8) if cap is None else cap
+        sub = np.zeros(ncap, np.uint8) if want_substep else None
+        self.s.substep_out = sub.ctypes.data if want_substep else None
         fn = lambda p, n, sym, soft, idx, lock, cap_: self.L.lrpt_oracle_process(
             C.byref(self.s), p, n, sym, soft, idx, lock, cap_)
-        return _run(fn, raw, self.bps, cap, want_float)
+        try:
+            res = _run(fn, raw, self.bps, ncap, want_float)
+        finally:
+            self.s.substep_out = None
+        if want_substep:
+            res["q"] = res.sample_idx * self.s.interp + sub[: res.sample_idx.size].astype(np.int64)
+        return res
 
     def taps(self):
         n = self.s.taps * self.s.interp

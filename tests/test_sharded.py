@@ -1,0 +1,241 @@
+"""Time-sharded single stream (Tier-S, meteor_demod_b200/sharded.py).
+
+CPU tests drive the stitch logic with chunks demodulated by the CPU oracle (same chunk plan the GPU
+engine uses), single process and as a 2-rank gloo job; the GPU test checks that the CUDA engine
+yields byte-identical stitched output to that oracle-driven run and reports the Tier-S epsilon
+against the sequential demodulation."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+CFG = dict(symrate=72000, oqpsk=0, bps=16, order=32, interp=5)
+N, CHUNK, WARM, OVERLAP = 1_900_000, 400_000, 160_000, 8192
+
+
+def make_stream():
+    from meteor_demod_b200 import synth
+    return synth.make_raw(N, cfo_hz=45.0, seed=77)
+
+
+def oracle_chunks(raw, plan, c0, c1):
+    """What GpuEngine.run returns, computed by the CPU oracle: soft [M,cap,2], q [M,cap] absolute, count [M]."""
+    from oracle import pyoracle
+    n_all = plan.n_main + plan.overlap
+    padded = np.zeros(2 * plan.padded, raw.dtype)
+    padded[: raw.size] = raw
+    outs = []
+    for c in range(c0, c1):
+        o = pyoracle.Oracle(**CFG)
+        s = plan.start(c)
+        w = o.process(padded[2 * s: 2 * (s + n_all)], want_float=False, want_substep=True)
+        outs.append((w.soft, w.q + s * plan.interp))
+    cap = max(x[0].shape[0] for x in outs) + 8
+    M = c1 - c0
+    soft = torch.zeros((M, cap, 2), dtype=torch.int8)
+    q = torch.zeros((M, cap), dtype=torch.int64)
+    count = torch.zeros(M, dtype=torch.int64)
+    for i, (s_, q_) in enumerate(outs):
+        n = s_.shape[0]
+        soft[i, :n] = torch.from_numpy(s_)
+        q[i, :n] = torch.from_numpy(q_)
+        count[i] = n
+    return soft, q, count
+
+
+def _rows(outs):
+    cap = max(x[0].shape[0] for x in outs) + 8
+    M = len(outs)
+    soft = torch.zeros((M, cap, 2), dtype=torch.int8)
+    q = torch.zeros((M, cap), dtype=torch.int64)
+    count = torch.zeros(M, dtype=torch.int64)
+    for i, (s_, q_) in enumerate(outs):
+        n = s_.shape[0]
+        soft[i, :n] = torch.from_numpy(s_)
+        q[i, :n] = torch.from_numpy(q_)
+        count[i] = n
+    return soft, q, count
+
+
+def oracle_two_pass(raw, plan):
+    """demod_sharded(two_pass=True) re-enacted with the CPU oracle: warm-up -> snapshot -> owned+overlap ->
+    quadrant scan -> same again from the snapshot with the Costas NCO turned back K_c quarter turns."""
+    import ctypes as C
+    from meteor_demod_b200 import sharded
+    from oracle import pyoracle
+    W, Cc, V, L = plan.warm, plan.chunk, plan.overlap, plan.interp
+    pad = np.zeros(2 * plan.padded, raw.dtype)
+    pad[: raw.size] = raw
+    snaps, outs_b, head = [], [], None
+    for c in range(plan.nchunks):
+        o = pyoracle.Oracle(**CFG)
+        s0 = plan.start(c)
+        wa = o.process(pad[2 * s0: 2 * (s0 + W)], want_float=False)
+        if c == 0:
+            head = wa.soft
+        snaps.append((o, bytes(o.s), o.history().copy()))
+        wb = o.process(pad[2 * (s0 + W): 2 * (s0 + W + Cc + V)], want_float=False, want_substep=True)
+        outs_b.append((wb.soft, wb.q + (s0 + W) * L))
+    scan = sharded.stitch(*_rows(outs_b), plan)
+    K = sharded.chunk_turns(scan, plan.nchunks)
+    outs_c = []
+    for c, (o, blob, hist) in enumerate(snaps):
+        C.memmove(C.byref(o.s), blob, len(blob))
+        o.set_history(hist)
+        # lrpt_restore: p_phase = (float)((double)p_phase - k*M_PI/2)
+        o.s.p_phase = float(np.float32(np.float64(np.float32(o.s.p_phase)) - float(int(K[c]) & 3) * 1.57079632679489661923))
+        s0 = plan.start(c)
+        wc = o.process(pad[2 * (s0 + W): 2 * (s0 + W + Cc + V)], want_float=False, want_substep=True)
+        outs_c.append((wc.soft, wc.q + (s0 + W) * L))
+    res = sharded.stitch(*_rows(outs_c), plan)
+    res["soft"] = torch.cat((torch.from_numpy(head), res["soft"]))
+    res["first_pass"] = dict(k=scan["k"], K=K)
+    return res
+
+
+def sequential(raw):
+    from oracle import pyoracle
+    return pyoracle.Oracle(**CFG).process(raw, want_float=False).soft
+
+
+def tier_s_report(stitched, seq):
+    n = min(len(stitched), len(seq))
+    d = np.abs(stitched[:n].astype(np.int16) - seq[:n].astype(np.int16)).max(axis=1)
+    return dict(n_stitched=len(stitched), n_seq=len(seq), frac_gt1=float((d > 1).mean()), frac_exact=float((d == 0).mean()))
+
+
+@pytest.fixture(scope="module")
+def stream():
+    return make_stream()
+
+
+@pytest.fixture(scope="module")
+def single(stream, oracle_mod):
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    soft, q, count = oracle_chunks(stream, plan, 0, plan.nchunks)
+    return plan, sharded.stitch(soft, q, count, plan)
+
+
+def test_plan_geometry():
+    from meteor_demod_b200 import sharded
+    p = sharded.Plan(N, CHUNK, WARM, OVERLAP, 5)
+    assert p.nchunks == 5 and p.boundary(0) == 0 and p.boundary(1) == WARM + CHUNK
+    assert p.boundary(p.nchunks - 1) < N <= WARM + p.nchunks * CHUNK
+    assert p.padded >= N and p.start(3) == 3 * CHUNK
+    assert [sharded.split_chunks(5, 2, r) for r in (0, 1)] == [(0, 3), (3, 5)]
+
+
+def test_rotation_is_exact_group_action():
+    from meteor_demod_b200.sharded import rotate_quarter_turns
+    s = torch.tensor([[5, -7], [127, -127], [0, 3]], dtype=torch.int8)
+    assert rotate_quarter_turns(s, 1).tolist() == [[7, 5], [127, 127], [-3, 0]]
+    assert torch.equal(rotate_quarter_turns(rotate_quarter_turns(s, 1), 3), s)
+    assert torch.equal(rotate_quarter_turns(s, torch.tensor([2, 2, 2])), -s)
+
+
+def test_single_process_stitch_matches_sequential_statistically(single, stream):
+    plan, res = single
+    seq = sequential(stream)
+    got = res["soft"].numpy()
+    rep = tier_s_report(got, seq)
+    assert rep["n_stitched"] == rep["n_seq"]                     # no symbol duplicated or dropped at any boundary
+    assert float(res["agreement"].min()) > 0.97                  # every boundary: chunks agree after de-rotation
+    # chunk 0 owns [0, W+C): bit exact with the sequential run
+    n0 = int((W0 := plan.boundary(1)) * 72000 / 230000) - 16
+    assert np.array_equal(got[:n0], seq[:n0])
+    assert rep["frac_gt1"] < 0.06, rep                           # Tier-S with a short 160k-sample warm-up (DESIGN.md has eps vs W)
+    print("Tier-S report:", rep, "k:", res["k"].tolist(), "agreement:", [round(x, 4) for x in res["agreement"].tolist()])
+
+
+def test_wrong_quadrant_would_be_detected(single, stream):
+    """Sanity of the metric: rotating one chunk by 90 degrees must show up as k changing by one."""
+    from meteor_demod_b200 import sharded
+    plan, res = single
+    soft, q, count = oracle_chunks(stream, plan, 0, plan.nchunks)
+    soft2 = soft.clone()
+    soft2[2] = sharded.rotate_quarter_turns(soft[2], 1)
+    res2 = sharded.stitch(soft2, q, count, plan)
+    dk = (res2["k"] - res["k"]) % 4
+    assert dk.tolist() == [0, 3, 1, 0]                           # boundary into chunk 2 undoes it, boundary out re-does
+    assert torch.equal(res2["soft"], res["soft"])                # and the stitched stream is unchanged
+
+
+def test_two_pass_reaches_reference_level_epsilon(stream):
+    """Turning every chunk's Costas NCO back to the sequential run's lock point makes all chunks see the
+    same Q arm in the timing detector: eps falls to the level of the reference's own FMA-vs-strict builds."""
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, 400_000, OVERLAP, CFG["interp"])
+    res = oracle_two_pass(stream, plan)
+    rep = tier_s_report(res["soft"].numpy(), sequential(stream))
+    assert rep["n_stitched"] == rep["n_seq"]
+    assert res["k"].tolist() == [0] * (plan.nchunks - 1)         # second pass: every boundary already aligned
+    assert float(res["agreement"].min()) > 0.995
+    assert rep["frac_gt1"] < 0.006, rep
+    print("two-pass Tier-S report:", rep, "first-pass K:", res["first_pass"]["K"].tolist())
+
+
+def _rank_main(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from meteor_demod_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    raw = make_stream()
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
+    soft, q, count = oracle_chunks(raw, plan, c0, c1)
+    res = sharded.stitch(soft, q, count, plan, first_chunk=c0, dist=dist)
+    np.save(os.path.join(out_dir, "part%d.npy" % rank), res["soft"].numpy())
+    np.save(os.path.join(out_dir, "meta%d.npy" % rank),
+            np.array([res["K_first"], res["K_last"], res["boundary_prev"][0] or 0], np.int64))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_equals_single_process(single, tmp_path):
+    """The N>1 path on CPU: 2 ranks, gloo, each owning a run of chunks; boundary symbols rank->rank+1 and
+    one all-gather of quarter turns. Concatenated output must equal the single-process stitch."""
+    import torch.multiprocessing as mp
+    plan, res = single
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(tmp_path / ("part%d.npy" % r)) for r in range(2)]
+    got = np.concatenate(parts)
+    assert np.array_equal(got, res["soft"].numpy())
+    meta1 = np.load(tmp_path / "meta1.npy")
+    K = np.concatenate([[0], np.cumsum(res["k"].numpy()) % 4])
+    assert meta1[0] == K[3] and meta1[1] == K[-1]                # rank 1 starts at chunk 3 with the right turn count
+
+
+@pytest.mark.gpu
+def test_gpu_two_pass_equals_oracle_two_pass(stream, lib):
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, 400_000, OVERLAP, CFG["interp"])
+    want = oracle_two_pass(stream, plan)
+    raw = torch.zeros(2 * plan.padded, dtype=torch.int16, device="cuda")
+    raw[: stream.size] = torch.from_numpy(stream).cuda()
+    out = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=400_000, overlap=OVERLAP, symrate=72000, bps=16,
+                                rrc_order=32, interp_factor=5, two_pass=True)
+    assert out["launches"] == 3                                  # warm-up, scan pass, final pass
+    assert torch.equal(out["first_pass"]["K"].cpu(), want["first_pass"]["K"])
+    assert out["k"].cpu().tolist() == [0] * (plan.nchunks - 1)
+    assert np.array_equal(out["soft"].cpu().numpy(), want["soft"].numpy())
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_equals_oracle_sharded(single, stream, lib):
+    from meteor_demod_b200 import sharded
+    plan, res = single
+    dev = torch.device("cuda")
+    raw = torch.zeros(2 * plan.padded, dtype=torch.int16, device=dev)
+    raw[: stream.size] = torch.from_numpy(stream).to(dev)
+    out = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
+                                rrc_order=32, interp_factor=5, two_pass=False)
+    assert out["plan"].nchunks == plan.nchunks and out["launches"] == 1
+    assert torch.equal(out["k"].cpu(), res["k"])
+    assert np.array_equal(out["soft"].cpu().numpy(), res["soft"].numpy())
