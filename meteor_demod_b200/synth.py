@@ -173,3 +173,38 @@ def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 7
             v = ((v * (rms * amp[b0:b1, None, None])) + dc).round().clamp(-32768, 32767)
             out[b0:b1] = v.reshape(b1 - b0, -1).to(dt)
     return out
+
+
+def device_long_stream(period, nsamples, total=None, bps=16, fs=230000, sps=230000 / 72000, seed=11, cfo_hz=700.0,
+                       phase=0.7, esn0_db=12.0, rms=6000.0, device="cuda", block=1 << 25):
+    """ONE long raw stream on the device (time-sharding workload): the tileable period repeated, a carrier
+    offset (rounded to a multiple of fs/len(period)), noise, quantisation. Returns a 1-D tensor with
+    2*total items (total >= nsamples; the tail beyond nsamples is zero padding)."""
+    import torch
+
+    dt = {8: torch.uint8, 16: torch.int16, 32: torch.float32}[bps]
+    total = nsamples if total is None else total
+    P = int(period.size)
+    base = torch.from_numpy(np.ascontiguousarray(period.astype(np.complex64))).to(device)
+    out = torch.zeros(2 * total, dtype=dt, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    step = fs / P
+    cfo = step * round(cfo_hz / step)
+    sigma = float(np.sqrt(sps / (10 ** (esn0_db / 10)) / 2)) if esn0_db is not None else 0.0
+    dc = torch.tensor([30.0, -20.0], device=device)
+    for n0 in range(0, nsamples, block):
+        n1 = min(nsamples, n0 + block)
+        n = torch.arange(n0, n1, device=device)
+        arg = torch.remainder(2 * np.pi / fs * cfo * n.to(torch.float64) + phase, 2 * np.pi).to(torch.float32)
+        y = base[n % P] * torch.polar(torch.ones_like(arg), arg)
+        if sigma:
+            y = y + sigma * torch.complex(torch.randn(y.shape, device=device, generator=g),
+                                          torch.randn(y.shape, device=device, generator=g))
+        v = torch.view_as_real(y)
+        if bps == 8:
+            v = ((v * (64.0 / 3.0)).round() + 128).clamp(0, 255)
+        else:
+            v = ((v * rms) + dc).round().clamp(-32768, 32767)
+        out[2 * n0: 2 * n1] = v.reshape(-1).to(dt)
+    return out
