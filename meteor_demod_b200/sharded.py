@@ -269,6 +269,7 @@ class GpuEngine:
         n_all = self.plan.n_main + self.plan.overlap
         self.d.reset(stream=stream, asynchronous=True)
         self.d.process_device(self._view(0, n_all), self.soft, nsym=self.nsym, stream=stream, nsamples=n_all)
+        self.d.sync(stream)                                  # the torch ops below run on torch's own stream
         return self._result(0)
 
     def warm_up(self):
@@ -324,9 +325,7 @@ def demod_sharded(raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, devi
     c0, c1 = split_chunks(plan.nchunks, world, rank)
     eng = GpuEngine(raw, plan, device=device, first_chunk=c0, nchunks=c1 - c0, **cfg)
     if not two_pass:
-        soft, q, count = eng.run()
-        eng.d.sync()
-        res = stitch(soft, q, count, plan, first_chunk=c0, dist=dist)
+        res = stitch(*eng.run(), plan, first_chunk=c0, dist=dist)
     else:
         head = eng.warm_up()
         scan = stitch(*eng.owned(), plan, first_chunk=c0, dist=dist)
