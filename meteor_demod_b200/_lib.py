@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "liblrpt_b200.so")
+SO_PATH = os.environ.get("LRPT_SO") or os.path.join(HERE, "liblrpt_b200.so")   # LRPT_SO: A/B builds while tuning
 
 LRPT_OK, LRPT_ERR_ARG, LRPT_ERR_CUDA, LRPT_ERR_NOMEM, LRPT_ERR_CAP, LRPT_ERR_STATE = 0, -1, -2, -3, -4, -5
 KERNELS = {"auto": 0, "simple": 1, "ws": 2}
