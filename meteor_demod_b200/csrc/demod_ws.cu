@@ -53,6 +53,7 @@ struct WsArgs {
 	int           G;           /* streams per CTA */
 	int           win;         /* delay-line window entries per stream: H + NT*T */
 	int           NT;          /* tiles per window epoch: 2 + ceil(H/T) */
+	int           nco_n0;      /* plain NCO adds before the tested window (multiple of 4) */
 };
 
 /* ------------------------------------------------------------- mbarrier ---- */
@@ -186,36 +187,45 @@ LRPT_DEV bool nco_chunk(Loop &r, const lrpt_consts_t &c, int &Q, int Qend, int &
 }
 
 /*
- * Run the timing NCO from sub-step Q to its next crossing, not beyond tile end q1 unless the
- * crossing search is a single predicted shot. In lock the number of sub-steps between crossings
- * repeats within +-1, so the previous count `guess` predicts this one: take guess-2 plain adds,
- * then test only the next three sums. Any surprise (acquisition transients, block end, a guess
- * that is off) falls back to the exhaustive chunks above, starting again from the untouched
- * phase. Either way the sums are the reference's float adds, in order.
+ * Run the timing NCO from sub-step Q to its next crossing. In steady state the number of sub-steps
+ * between two crossings is pi-or-2pi / t_center within +-1 (the NCO step is clamped to +-2^-12 of its
+ * centre, timing.c:7,84), so the launch fixes n0 = a multiple of 4 safely below that count: n0 plain
+ * float adds (warp-uniform loop, no compares), then NCO_WINDOW tested sums, branch-free. The search
+ * is accepted only if the crossing provably lies inside the window (no sum before it had crossed,
+ * one inside did); otherwise -- acquisition transients, end of block, imported odd states -- the
+ * exhaustive chunks above run from the untouched phase. The sums are the reference's adds, in order.
  */
-LRPT_DEV bool nco_to_crossing(Loop &r, const lrpt_consts_t &c, int &Q, int q1, int Qend,
-                              int &Qx, int &half, int &guess)
+constexpr int NCO_WINDOW = 8;
+
+LRPT_DEV bool nco_to_crossing(Loop &r, const lrpt_consts_t &c, int n0, int &Q, int q1, int Qend,
+                              int &Qx, int &half)
 {
 	const float f = r.t_freq;
 	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
-	const int n = guess - 2;
-	if (f > 0.0f && n >= 0 && Q + n + 3 <= Qend) {
-		float p = r.t_phase;
-		for (int j = 0; j < n; j++) p = __fadd_rn(p, f);
-		const float p1 = __fadd_rn(p, f), p2 = __fadd_rn(p1, f), p3 = __fadd_rn(p2, f);
-		if (!(p >= thr) && p3 >= thr) {
-			const bool h1 = p1 >= thr, h2 = p2 >= thr;
-			const int k = h1 ? 1 : (h2 ? 2 : 3);
-			r.t_phase = h1 ? p1 : (h2 ? p2 : p3);
-			Qx = Q + n + k - 1; Q += n + k; guess = n + k;
-			if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
-			return true;
-		}
+	float p = r.t_phase;
+	for (int b = 0; b < n0; b += 4) {                               /* n0 is warp-uniform and a multiple of 4 */
+		p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f);
 	}
-	const int start = Q;
+	float s[NCO_WINDOW];
+	float acc = p;
+	int below = 0;
+#pragma unroll
+	for (int j = 0; j < NCO_WINDOW; j++) {
+		acc = __fadd_rn(acc, f);
+		s[j] = acc;
+		below += (acc >= thr) ? 0 : 1;
+	}
+	float sel = s[NCO_WINDOW-1];
+#pragma unroll
+	for (int j = NCO_WINDOW - 2; j >= 0; j--) sel = (s[j] >= thr) ? s[j] : sel;
+	if (f > 0.0f && !(p >= thr) && below < NCO_WINDOW && Q + n0 + NCO_WINDOW <= Qend) {
+		r.t_phase = sel;
+		Qx = Q + n0 + below; Q = Qx + 1;
+		if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
+		return true;
+	}
 	bool found = false;
 	while (!found && Q < q1) found = nco_chunk(r, c, Q, Qend, Qx, half);
-	if (found) guess = Q - start;
 	return found;
 }
 
@@ -280,7 +290,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		}
 		const int Qend = a.nsamples*L;          /* total timing sub-steps of this launch */
 		int Q = 0;                              /* sub-steps already taken               */
-		bool have_x = false; int Qx = 0, half = 0, guess = 0;
+		bool have_x = false; int Qx = 0, half = 0;
 		const float2 *my_tiles = tiles + (size_t)lane*S*T*L;
 
 		for (int t = 0; t < ntiles; t++) {
@@ -295,7 +305,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 				 * lane holding a crossing inside the tile takes its symbol step, all together. */
 				while (true) {
 					if (active && !have_x && Q < q1)
-						have_x = nco_to_crossing(r, c, Q, q1, Qend, Qx, half, guess);
+						have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
 					__syncwarp();
 					const bool ready = active && have_x && Qx < q1;
 					if (!__any_sync(0xffffffffu, ready)) break;
@@ -511,6 +521,12 @@ cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches)
 		w.cap = a.cap; w.nsym_out = a.d_nsym; w.out_off = a.d_out_off;
 		w.first_stream = a.first_stream; w.nstreams = a.nstreams; w.G = G;
 		w.win = ws_win(taps); w.NT = ws_nt(taps);
+		{
+			/* sub-steps between timing events: 2*pi/step (QPSK) or pi/step (OQPSK halves) */
+			const double nominal = (c.oqpsk ? 3.14159265358979 : 6.28318530717959)/(double)c.t_center;
+			const int cmin = (int)nominal - 1;
+			w.nco_n0 = cmin > 1 ? 4*((cmin - 1)/4) : 0;
+		}
 		const size_t smem = fixed + per*(size_t)G;
 		switch (L) {
 			case 1: ws_launch_one<1>(c, w, blocks, smem, st); break;
