@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
                     help="batch: independent streams (exact); sharded: ONE stream of --stream-samples per job, "
                          "time-sharded over chunks and GPUs (Tier-S, reports eps)")
-    ap.add_argument("--stream-samples", type=int, default=1 << 28)
+    ap.add_argument("--stream-samples", type=int, default=1 << 30)
     ap.add_argument("--chunk", type=int, default=1 << 18)
     ap.add_argument("--warm", type=int, default=400000)
     ap.add_argument("--single-pass", action="store_true")
@@ -329,7 +329,17 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        # context for the e2e number: what the host link alone does with the same pinned buffer
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        raw.copy_(h_raw, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = h_raw.numel() * h_raw.element_size() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
         e2e = {"value": world * B * N * a.steps / dt / 1e6, "unit": "Msamples/s",
+               "h2d_link_gbs": h2d_gbs,
+               "link_bound_msps": h2d_gbs * 1e9 / (bps // 4) / 1e6 * world,
                "h2d_bytes_per_step": int(B * N * (bps // 4)), "d2h_bytes_per_step": int(2 * int(h_cnt.max()) * B + 4 * B),
                "ms_per_step": 1e3 * dt / a.steps,
                "matches_device_path": bool(np.array_equal(h_cnt.astype(np.int64), counts))}
@@ -393,16 +403,17 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    sd = sharded.ShardedDemod(raw, N, **kw)
     res = None
     for _ in range(a.warmup):
-        res = sharded.demod_sharded(raw, N, **kw)
+        res = sd.run()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with Clocks(local) as clk:
         e0.record()
         launches = 0
         for _ in range(a.steps):
-            res = sharded.demod_sharded(raw, N, **kw)
+            res = sd.run()
             launches += res["launches"]
         e1.record()
         barrier()

@@ -289,9 +289,11 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 	if (!h || (!raw_iq && nsamples) || !soft || cap > 0xffffffffu) return LRPT_ERR_ARG;
 	CU(h, cudaSetDevice(h->p.device));
 	const size_t bpsm = bytes_per_sample(h);
-	/* slab: about 64 MiB of raw input across the batch, at least 64 Ki samples per stream */
-	size_t slab = ((size_t)64 << 20)/(bpsm*(size_t)count);
-	if (slab < 65536) slab = 65536;
+	/* slab: about 256 MiB of raw input across the batch, at least 16 Ki samples per stream: small enough
+	 * that the first copy (nothing to overlap with) and the last kernel are short, large enough that a
+	 * launch still runs hundreds of tiles */
+	size_t slab = ((size_t)256 << 20)/(bpsm*(size_t)count);
+	if (slab < 16384) slab = 16384;
 	slab = round_up(slab, 4096);
 	if (slab > nsamples) slab = round_up(nsamples ? nsamples : 1, 16);
 	const size_t d_raw_pitch = round_up(slab*bpsm, 256);

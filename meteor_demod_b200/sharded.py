@@ -299,10 +299,46 @@ class GpuEngine:
         self.d.close()
 
 
-def demod_sharded(raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
-                  interp_factor=5, two_pass=True, **cfg):
-    """One long stream, time-sharded over this process's GPU and, with `dist` (torch.distributed,
-    initialised), over ranks: rank r takes a consecutive run of chunks and reads them from ITS copy of
+class ShardedDemod:
+    """Persistent time-sharding engine for one stream buffer (plan, device buffers and the C-ABI handle
+    are built once; run() can be called repeatedly, e.g. by bench.py)."""
+
+    def __init__(self, raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
+                 interp_factor=5, two_pass=True, **cfg):
+        if cfg.get("oqpsk"):
+            raise NotImplementedError("time-sharding resolves the k*90 degree ambiguity of QPSK only")
+        self.plan = plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
+        self.dist, self.two_pass = dist, two_pass
+        world = dist.get_world_size() if dist is not None else 1
+        rank = dist.get_rank() if dist is not None else 0
+        if plan.nchunks < world:
+            raise ValueError("fewer chunks (%d) than ranks (%d)" % (plan.nchunks, world))
+        self.c0, self.c1 = split_chunks(plan.nchunks, world, rank)
+        self.eng = GpuEngine(raw, plan, device=device, first_chunk=self.c0, nchunks=self.c1 - self.c0, **cfg)
+
+    def run(self):
+        eng, plan, c0, M = self.eng, self.plan, self.c0, self.c1 - self.c0
+        l0 = eng.d.launch_count()
+        if not self.two_pass:
+            res = stitch(*eng.run(), plan, first_chunk=c0, dist=self.dist)
+        else:
+            head = eng.warm_up()
+            scan = stitch(*eng.owned(), plan, first_chunk=c0, dist=self.dist)
+            K = chunk_turns(scan, M)
+            res = stitch(*eng.owned(K), plan, first_chunk=c0, dist=self.dist)
+            res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
+            if c0 == 0:
+                res["soft"] = torch.cat((head, res["soft"]))
+        res.update(plan=plan, first_chunk=c0, nchunks_local=M, launches=eng.d.launch_count() - l0)
+        return res
+
+    def close(self):
+        self.eng.close()
+
+
+def demod_sharded(raw, nsamples, **kw):
+    """One long stream, time-sharded over this process's GPU and, with dist=torch.distributed
+    (initialised), over ranks: rank r takes a consecutive run of chunks and reads them from ITS copy of
     the stream (over-reading warm-up and overlap instead of communicating samples). raw: 1-D device
     tensor of the raw dtype with at least 2*Plan.padded items (zeros after 2*nsamples).
 
@@ -314,26 +350,10 @@ def demod_sharded(raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, devi
     again from the snapshot with every Costas NCO turned back by its K_c quarter turns, so all chunks
     run at the sequential run's lock point: eps drops to the 0.2-0.4 % of the reference's own
     FMA-vs-strict builds, at the price of demodulating the owned samples twice.
-    Returns the stitch() dict plus plan, first_chunk, nchunks_local, launches."""
-    if cfg.get("oqpsk"):
-        raise NotImplementedError("time-sharding resolves the k*90 degree ambiguity of QPSK only")
-    plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
-    world = dist.get_world_size() if dist is not None else 1
-    rank = dist.get_rank() if dist is not None else 0
-    if plan.nchunks < world:
-        raise ValueError("fewer chunks (%d) than ranks (%d)" % (plan.nchunks, world))
-    c0, c1 = split_chunks(plan.nchunks, world, rank)
-    eng = GpuEngine(raw, plan, device=device, first_chunk=c0, nchunks=c1 - c0, **cfg)
-    if not two_pass:
-        res = stitch(*eng.run(), plan, first_chunk=c0, dist=dist)
-    else:
-        head = eng.warm_up()
-        scan = stitch(*eng.owned(), plan, first_chunk=c0, dist=dist)
-        K = chunk_turns(scan, c1 - c0)
-        res = stitch(*eng.owned(K), plan, first_chunk=c0, dist=dist)
-        res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
-        if c0 == 0:
-            res["soft"] = torch.cat((head, res["soft"]))
-    res.update(plan=plan, first_chunk=c0, nchunks_local=c1 - c0, launches=eng.d.launch_count())
-    eng.close()
-    return res
+    Keyword arguments: chunk, warm, overlap, device, dist, interp_factor, two_pass + Demod's (symrate,
+    bps, rrc_order, ...). Returns the stitch() dict plus plan, first_chunk, nchunks_local, launches."""
+    sd = ShardedDemod(raw, nsamples, **kw)
+    try:
+        return sd.run()
+    finally:
+        sd.close()
