@@ -61,6 +61,12 @@ class Plan:
     def boundary(self, c):         # B_c: first sample chunk c owns (chunk 0 owns from 0)
         return 0 if c == 0 else self.warm + c * self.chunk
 
+    def cut_target(self, c):
+        """Sub-step index around which chunks c-1 and c are joined: a little INSIDE chunk c's owned region,
+        so that both rows have symbols on either side of the cut (in the two-pass scheme row c only starts
+        at B_c; a symbol instant falling exactly on B_c is in one row and not the other)."""
+        return (self.boundary(c) + min(64, self.overlap // 4)) * self.interp
+
     @property
     def n_main(self):              # samples up to the successor's boundary
         return self.warm + self.chunk
@@ -148,7 +154,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
     world = dist.get_world_size() if dist is not None else 1
     M, L, dev = soft.shape[0], plan.interp, soft.device
     big = torch.iinfo(torch.int64).max
-    Bq = torch.tensor([plan.boundary(first_chunk + c) * L for c in range(1, M)], dtype=torch.int64, device=dev)
+    Bq = torch.tensor([plan.cut_target(first_chunk + c) for c in range(1, M)], dtype=torch.int64, device=dev)
     k, agree, cut = boundary_quadrants(soft, q, count, Bq)
 
     k_prev, agree_prev, cut_prev = 0, None, None
@@ -158,7 +164,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
         pack = torch.zeros((width, 3), dtype=torch.int64, device=dev)
         npack = torch.zeros(1, dtype=torch.int64, device=dev)
         if first_chunk + M < plan.nchunks:
-            nextB = plan.boundary(first_chunk + M) * L
+            nextB = plan.cut_target(first_chunk + M)
             n = int(count[-1].item())
             sel = (q[-1, :n] >= nextB - 64 * L).nonzero().squeeze(1)[:width]
             pack[: sel.numel(), 0] = q[-1, sel]
@@ -182,7 +188,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
             two_q[1, : soft.shape[1]] = q[0]
             two_n = torch.stack((torch.tensor(n, dtype=torch.int64, device=dev), count[0]))
             kp, ap, cp = boundary_quadrants(two_s, two_q, two_n,
-                                            torch.tensor([plan.boundary(first_chunk) * L], device=dev))
+                                            torch.tensor([plan.cut_target(first_chunk)], device=dev))
             k_prev, agree_prev, cut_prev = int(kp[0].item()), float(ap[0].item()), int(cp[0].item())
 
     # (b) prefix sum of quarter turns over ranks
@@ -206,7 +212,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
         hi[:-1] = cut
     if first_chunk + M < plan.nchunks:
         # my last chunk ends where the next rank's first chunk begins: same rule, evaluated locally
-        nextB = torch.tensor([plan.boundary(first_chunk + M) * L], dtype=torch.int64, device=dev)
+        nextB = torch.tensor([plan.cut_target(first_chunk + M)], dtype=torch.int64, device=dev)
         ia = _first_at_or_after(q[-1:], count[-1:], nextB)
         pq = torch.gather(q[-1:], 1, (ia - 1).clamp(min=0)[:, None]).squeeze(1)
         nq = torch.gather(q[-1:], 1, ia.clamp(max=q.shape[1] - 1)[:, None]).squeeze(1)

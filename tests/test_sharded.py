@@ -138,6 +138,41 @@ def test_rotation_is_exact_group_action():
     assert torch.equal(rotate_quarter_turns(s, torch.tensor([2, 2, 2])), -s)
 
 
+def test_symbol_instant_exactly_on_the_boundary_is_neither_lost_nor_doubled():
+    """Two-pass rows start AT their boundary. If the predecessor has a symbol instant exactly on it while
+    the successor's clock is one sub-step early (that symbol then fell into its warm-up), joining at the
+    boundary itself would drop the symbol; the cut target lies 64 samples inside instead."""
+    from meteor_demod_b200 import sharded
+    L, C, W, V = 5, 4096, 1024, 512
+    plan = sharded.Plan(3 * C + W, C, W, V, L)                     # 3 chunks
+    period = 16
+
+    def row(first_q, last_q, shift, base_index):
+        q = torch.arange(first_q, last_q, period, dtype=torch.int64) + shift
+        idx = (q - shift) // period - base_index                   # global symbol number of the instant
+        soft = torch.stack(((idx % 100).to(torch.int8), ((idx // 100) % 100).to(torch.int8)), dim=1)
+        return soft, q
+    B1, B2 = plan.boundary(1) * L, plan.boundary(2) * L
+    assert B1 % period == 0 and B2 % period == 0                   # symbol instants fall exactly on both boundaries
+    r0 = row(W * L, B1 + V * L, 0, 0)                              # chunk 0: instants on the grid, one exactly at B1
+    r1 = row(B1 + period, B2 + V * L, -1, 0)                       # chunk 1: one sub-step early => no symbol at/after B1 before B1+15
+    r2 = row(B2, 3 * C * L + W * L, +1, 0)                         # chunk 2: one sub-step late
+    cap = max(len(r[1]) for r in (r0, r1, r2))
+    soft = torch.zeros((3, cap, 2), dtype=torch.int8)
+    q = torch.zeros((3, cap), dtype=torch.int64)
+    count = torch.zeros(3, dtype=torch.int64)
+    for i, (s_, q_) in enumerate((r0, r1, r2)):
+        soft[i, : len(q_)] = s_
+        q[i, : len(q_)] = q_
+        count[i] = len(q_)
+    res = sharded.stitch(soft, q, count, plan)
+    out = res["soft"].to(torch.int64)
+    idx = out[:, 0] + 100 * out[:, 1]
+    d = (idx[1:] - idx[:-1]) % 10000
+    assert torch.all(d == 1), "gap or duplicate at a boundary: %s" % d[d != 1].tolist()
+    assert res["k"].tolist() == [0, 0] and float(res["agreement"].min()) == 1.0
+
+
 def test_single_process_stitch_matches_sequential_statistically(single, stream):
     plan, res = single
     seq = sequential(stream)
