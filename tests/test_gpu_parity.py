@@ -170,3 +170,53 @@ def test_edge_inputs(kernel, oracle_mod, lib):
         assert np.array_equal(bits(symf[0, :w.nsym]), bits(w.sym))
         assert np.array_equal(soft[0, :w.nsym], w.soft)
         assert_state_equal(d.state(), o)
+
+
+def test_configurations_outside_the_fast_kernel_fall_back_exactly(oracle_mod, lib):
+    """interp > 8 or taps > 257 are served by the simple kernel under LRPT_KERNEL_AUTO; asking for the
+    warp-specialised kernel explicitly is refused. Results stay bit-exact."""
+    from meteor_demod_b200 import Demod, LrptError
+    for cfg in (dict(symrate=72000, oqpsk=0, bps=16, order=140, interp=5), dict(symrate=72000, oqpsk=1, bps=8, order=20, interp=11)):
+        raw = make_case("C2_oqpsk80k_u8_o32_L5" if cfg["bps"] == 8 else "C1_qpsk72k_s16_o32_L5", 20_000, seed=3)
+        d = Demod(symrate=cfg["symrate"], oqpsk=cfg["oqpsk"], bps=cfg["bps"], rrc_order=cfg["order"],
+                  interp_factor=cfg["interp"], kernel="auto")
+        assert d.kernel_name() == "simple"
+        soft, counts, symf = d.process_batch(raw.reshape(1, -1), want_float=True)
+        o = oracle_mod.Oracle(**cfg)
+        w = o.process(raw)
+        assert counts[0] == w.nsym and np.array_equal(bits(symf[0, :w.nsym]), bits(w.sym))
+        assert_state_equal(d.state(), o)
+        with pytest.raises(LrptError):
+            Demod(symrate=cfg["symrate"], oqpsk=cfg["oqpsk"], bps=cfg["bps"], rrc_order=cfg["order"],
+                  interp_factor=cfg["interp"], kernel="ws")
+
+
+def test_long_push_is_split_transparently(lib):
+    """More samples than one launch addresses with int32 sub-step indices (2^26): the library cuts the push
+    into several launches; the result must equal two half-size pushes (state + append cursor carried)."""
+    import torch
+    from meteor_demod_b200 import Demod, synth
+    n = (1 << 26) + 300_000
+    per = synth.baseband(230000, periodic=True, seed=3).astype(np.complex64)
+    raw = synth.device_long_stream(per, n, cfo_hz=90.0).view(1, -1)
+    d1 = Demod(nstreams=1)
+    cap = (d1.capacity(n) + 7) // 8 * 8
+    s1 = torch.zeros((1, 2 * cap), dtype=torch.int8, device="cuda")
+    l0 = d1.launch_count()
+    d1.process_device(raw, s1)
+    d1.sync()
+    assert d1.launch_count() - l0 == 2
+    n1 = int(d1.counts()[0])
+    d2 = Demod(nstreams=1)
+    half = (n // 2) // 8 * 8
+    sa = torch.zeros((1, 2 * cap), dtype=torch.int8, device="cuda")
+    sb = torch.zeros((1, 2 * cap), dtype=torch.int8, device="cuda")
+    d2.process_device(raw[:, : 2 * half].contiguous(), sa)
+    d2.sync()
+    na = int(d2.counts()[0])
+    d2.process_device(raw[:, 2 * half:].contiguous(), sb)
+    d2.sync()
+    nb = int(d2.counts()[0])
+    assert n1 == na + nb
+    assert torch.equal(s1[0, : 2 * na], sa[0, : 2 * na]) and torch.equal(s1[0, 2 * na: 2 * n1], sb[0, : 2 * nb])
+    assert d1.export_state() == d2.export_state()
