@@ -494,8 +494,13 @@ static int ws_pick_g(int nstreams, size_t fixed, size_t per)
 	int gfit = (int)(((size_t)g_max_smem - fixed)/per);
 	if (gfit < 1) return 0;
 	gfit = std::min(gfit, WS_MAX_G);
-	int G = (nstreams + g_num_sms*WS_CTAS_PER_SM - 1)/(g_num_sms*WS_CTAS_PER_SM);
-	return std::max(1, std::min(G, gfit));
+	const int slots = g_num_sms*WS_CTAS_PER_SM;
+	int G = std::max(1, std::min((nstreams + slots - 1)/slots, gfit));
+	/* when shared memory caps G below that, the grid needs several waves: level them instead of
+	 * running one full wave and a nearly empty one */
+	const int blocks = (nstreams + G - 1)/G;
+	const int waves = (blocks + slots - 1)/slots;
+	return std::max(1, (nstreams + waves*slots - 1)/(waves*slots));
 }
 
 cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches)
