@@ -49,7 +49,7 @@ enum {
 
 /* Which kernel runs the recurrence. AUTO picks the warp-specialised kernel when the
  * configuration fits it and the simple one otherwise; results are bit-identical. */
-enum { LRPT_KERNEL_AUTO = 0, LRPT_KERNEL_SIMPLE = 1, LRPT_KERNEL_WS = 2 };
+enum { LRPT_KERNEL_AUTO = 0, LRPT_KERNEL_SIMPLE = 1, LRPT_KERNEL_WS = 2, LRPT_KERNEL_SPEC = 3 };
 
 typedef struct lrpt_demod lrpt_demod_t;       /* opaque; owns device buffers + a CUDA stream */
 
@@ -188,7 +188,10 @@ int  lrpt_get_taps(const lrpt_demod_t *h, float *dst, int cap);   /* returns tap
 int  lrpt_get_tanh_lut(const lrpt_demod_t *h, float dst[32]);
 /* number of CUDA kernels this handle has launched so far */
 unsigned long long lrpt_launch_count(const lrpt_demod_t *h);
-/* name of the kernel AUTO resolved to ("simple" | "ws") */
+/* FIR outputs the recurrence had to evaluate itself because the speculative FIR warps had not (spec kernel;
+ * a cost indicator, never a correctness matter) */
+unsigned long long lrpt_fir_fallbacks(lrpt_demod_t *h);
+/* name of the kernel AUTO resolved to ("simple" | "ws" | "spec") */
 const char *lrpt_kernel_name(const lrpt_demod_t *h);
 const char *lrpt_last_error(const lrpt_demod_t *h);  /* human-readable detail of the last failure */
 const char *lrpt_strerror(int code);

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("LRPT_SO") or os.path.join(HERE, "liblrpt_b200.so")   # LRPT_SO: A/B builds while tuning
 
 LRPT_OK, LRPT_ERR_ARG, LRPT_ERR_CUDA, LRPT_ERR_NOMEM, LRPT_ERR_CAP, LRPT_ERR_STATE = 0, -1, -2, -3, -4, -5
-KERNELS = {"auto": 0, "simple": 1, "ws": 2}
+KERNELS = {"auto": 0, "simple": 1, "ws": 2, "spec": 3}
 
 
 class Params(C.Structure):
@@ -63,6 +63,7 @@ SYMBOLS = {
     "lrpt_get_taps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lrpt_get_tanh_lut": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lrpt_launch_count": (C.c_ulonglong, [C.c_void_p]),
+    "lrpt_fir_fallbacks": (C.c_ulonglong, [C.c_void_p]),
     "lrpt_kernel_name": (C.c_char_p, [C.c_void_p]),
     "lrpt_last_error": (C.c_char_p, [C.c_void_p]),
     "lrpt_strerror": (C.c_char_p, [C.c_int]),

@@ -20,23 +20,18 @@
  * samples is read from HBM and nothing but soft symbols (+ state) is written.
  */
 #include <algorithm>
-#include "demod_core.cuh"
+#include "ws_common.cuh"
 #include "kernels.h"
 
 namespace lrpt {
 
 constexpr int WS_T        = 32;    /* samples per tile = one FIR unit per stream  */
 constexpr int WS_SLOTS    = 2;     /* FIR tile ring depth                        */
-constexpr int WS_WARPS    = 16;    /* warps per CTA                              */
-constexpr int WS_PRODUCERS = 12;   /* FIR warps: the ones NOT on SM sub-partition 0 (warp id % 4 != 0)       */
-constexpr int WS_THREADS  = 32*WS_WARPS;
 constexpr int WS_MAX_G    = 32;    /* streams per CTA = consumer lanes           */
 constexpr int WS_CTAS_PER_SM = 1;  /* one big CTA per SM: the recurrence warp's time per symbol does not
                                       depend on how many of its 32 lanes carry a stream, so lanes are filled first */
-constexpr int NCO_CHUNK   = 8;     /* timing sub-steps evaluated per branch      */
 constexpr int WS_MAX_TAPS = 257;
 constexpr int WS_MAX_L    = 8;
-constexpr int WS_MAX_SAMPLES = 1 << 26;   /* per launch; keeps sub-step indices in int32 */
 
 struct WsArgs {
 	const float  *taps;
@@ -55,53 +50,6 @@ struct WsArgs {
 	int           NT;          /* tiles per window epoch: 2 + ceil(H/T) */
 	int           nco_n0;      /* plain NCO adds before the tested window (multiple of 4) */
 };
-
-/* ------------------------------------------------------------- mbarrier ---- */
-
-LRPT_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-LRPT_DEV void mbar_init(uint64_t *bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-
-LRPT_DEV void mbar_arrive(uint64_t *bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-
-LRPT_DEV void mbar_wait(uint64_t *bar, unsigned parity)
-{
-	asm volatile(
-		"{\n\t.reg .pred p;\n\t"
-		"WAIT_%=:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra DONE_%=;\n\t"
-		"bra WAIT_%=;\n\t"
-		"DONE_%=:\n\t}"
-		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-/* Producers wait here for the recurrence warp most of the time; back off between polls so
- * their polling does not take issue slots away from that warp, which is the critical path. */
-LRPT_DEV void mbar_wait_relaxed(uint64_t *bar, unsigned parity)
-{
-	unsigned done;
-	for (;;) {
-		asm volatile(
-			"{\n\t.reg .pred p;\n\t"
-			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-			"selp.u32 %0, 1, 0, p;\n\t}"
-			: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-		if (done) break;
-		__nanosleep(200);
-	}
-}
-
-LRPT_DEV void producers_sync()
-{
-	asm volatile("bar.sync 1, %0;" :: "n"(32*WS_PRODUCERS) : "memory");
-}
 
 /* ------------------------------------------------------------- producer ---- */
 
@@ -138,96 +86,6 @@ LRPT_DEV void fir_all_phases(const float2 *__restrict__ w, const float *__restri
 }
 
 /* ------------------------------------------------------------- kernel ------ */
-
-/*
- * One chunk of advance_timeslot (timing.c:32-38) / advance_timeslot_dual (:41-57):
- * up to NCO_CHUNK float additions of the NCO step, stopping at the first sum that
- * reaches the threshold. Fast path (step > 0, at least NCO_CHUNK sub-steps left):
- * the sums are non-decreasing, so the number of sums below the threshold IS the
- * index of the first crossing -- no bit scan, no data-dependent branch inside.
- * Returns true when a crossing was found; Qx = its sub-step index.
- */
-LRPT_DEV bool nco_chunk(Loop &r, const lrpt_consts_t &c, int &Q, int Qend, int &Qx, int &half)
-{
-	const float f = r.t_freq;
-	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
-	const int limit = Qend - Q;                                     /* >= 1 */
-	bool found;
-	if (f > 0.0f && limit >= NCO_CHUNK) {
-		float ph[NCO_CHUNK];
-		float acc = r.t_phase;
-		int below = 0;
-#pragma unroll
-		for (int j = 0; j < NCO_CHUNK; j++) {
-			acc = __fadd_rn(acc, f);
-			ph[j] = acc;
-			below += (acc >= thr) ? 0 : 1;
-		}
-		float sel = ph[NCO_CHUNK-1];
-#pragma unroll
-		for (int j = NCO_CHUNK - 2; j >= 0; j--) sel = (ph[j] >= thr) ? ph[j] : sel;
-		r.t_phase = sel;                                            /* first sum >= thr, or the last sum */
-		found = below < NCO_CHUNK;
-		Qx = Q + below;
-		Q += found ? below + 1 : NCO_CHUNK;
-	} else {
-		/* end of the block, or a non-positive step from an imported state: one sub-step at a time */
-		found = false;
-		const int n = min(limit, NCO_CHUNK);
-		float acc = r.t_phase;
-		for (int j = 0; j < n && !found; j++) {
-			acc = __fadd_rn(acc, f);
-			Qx = Q; Q++;
-			found = acc >= thr;
-		}
-		r.t_phase = acc;
-	}
-	if (found && c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
-	return found;
-}
-
-/*
- * Run the timing NCO from sub-step Q to its next crossing. In steady state the number of sub-steps
- * between two crossings is pi-or-2pi / t_center within +-1 (the NCO step is clamped to +-2^-12 of its
- * centre, timing.c:7,84), so the launch fixes n0 = a multiple of 4 safely below that count: n0 plain
- * float adds (warp-uniform loop, no compares), then NCO_WINDOW tested sums, branch-free. The search
- * is accepted only if the crossing provably lies inside the window (no sum before it had crossed,
- * one inside did); otherwise -- acquisition transients, end of block, imported odd states -- the
- * exhaustive chunks above run from the untouched phase. The sums are the reference's adds, in order.
- */
-constexpr int NCO_WINDOW = 8;
-
-LRPT_DEV bool nco_to_crossing(Loop &r, const lrpt_consts_t &c, int n0, int &Q, int q1, int Qend,
-                              int &Qx, int &half)
-{
-	const float f = r.t_freq;
-	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
-	float p = r.t_phase;
-	for (int b = 0; b < n0; b += 4) {                               /* n0 is warp-uniform and a multiple of 4 */
-		p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f);
-	}
-	float s[NCO_WINDOW];
-	float acc = p;
-	int below = 0;
-#pragma unroll
-	for (int j = 0; j < NCO_WINDOW; j++) {
-		acc = __fadd_rn(acc, f);
-		s[j] = acc;
-		below += (acc >= thr) ? 0 : 1;
-	}
-	float sel = s[NCO_WINDOW-1];
-#pragma unroll
-	for (int j = NCO_WINDOW - 2; j >= 0; j--) sel = (s[j] >= thr) ? s[j] : sel;
-	if (f > 0.0f && !(p >= thr) && below < NCO_WINDOW && Q + n0 + NCO_WINDOW <= Qend) {
-		r.t_phase = sel;
-		Qx = Q + n0 + below; Q = Qx + 1;
-		if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
-		return true;
-	}
-	bool found = false;
-	while (!found && Q < q1) found = nco_chunk(r, c, Q, Qend, Qx, half);
-	return found;
-}
 
 template <int L, bool OQ>
 __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM)

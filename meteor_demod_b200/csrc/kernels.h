@@ -37,4 +37,9 @@ bool        ws_supported(const lrpt_consts_t &c);
 cudaError_t ws_prepare(int device);                       /* one-time attribute setup */
 cudaError_t launch_ws(const LaunchArgs &a, cudaStream_t st, int *launches);
 
+/* speculative-FIR kernel (demod_spec.cu) */
+bool        spec_supported(const lrpt_consts_t &c);
+cudaError_t spec_prepare(int device);
+cudaError_t launch_spec(const LaunchArgs &a, cudaStream_t st, int *launches, unsigned long long *d_fallbacks);
+
 } // namespace lrpt

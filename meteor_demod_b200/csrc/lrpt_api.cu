@@ -31,6 +31,7 @@ struct lrpt_demod {
 	float2       *d_hist   = nullptr;
 	uint32_t     *d_nsym   = nullptr;   /* [nstreams] last launch */
 	uint32_t     *d_off    = nullptr;   /* [nstreams] append cursors (host-buffer path) */
+	unsigned long long *d_fallbacks = nullptr;   /* spec kernel: FIR evaluations done by the recurrence warp */
 	uint32_t     *h_counts = nullptr;   /* pinned [nstreams] */
 	lrpt_state_t *d_init   = nullptr;   /* [nstreams] power-on states, source of resets */
 	lrpt_state_t *d_snap   = nullptr;   /* [nstreams] lrpt_snapshot */
@@ -140,6 +141,8 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 	CUC(cudaMalloc(&h->d_hist, sizeof(float2)*(size_t)(h->H > 0 ? h->H : 1)*p->nstreams));
 	CUC(cudaMalloc(&h->d_nsym, sizeof(uint32_t)*p->nstreams));
 	CUC(cudaMalloc(&h->d_off, sizeof(uint32_t)*p->nstreams));
+	CUC(cudaMalloc(&h->d_fallbacks, sizeof(unsigned long long)));
+	CUC(cudaMemset(h->d_fallbacks, 0, sizeof(unsigned long long)));
 	CUC(cudaMallocHost(&h->h_counts, sizeof(uint32_t)*p->nstreams));
 	CUC(cudaMallocHost(&h->h_state, sizeof(lrpt_state_t)));
 	CUC(cudaMemcpy(h->d_taps, h->taps.data(), sizeof(float)*h->taps.size(), cudaMemcpyHostToDevice));
@@ -149,7 +152,14 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 		fprintf(stderr, "lrpt_create: configuration not supported by the warp-specialised kernel\n");
 		lrpt_destroy(h); return LRPT_ERR_ARG;
 	}
-	if (p->kernel != LRPT_KERNEL_SIMPLE && ws_supported(h->c)) {
+	if (p->kernel == LRPT_KERNEL_SPEC && !spec_supported(h->c)) {
+		fprintf(stderr, "lrpt_create: configuration not supported by the speculative-FIR kernel\n");
+		lrpt_destroy(h); return LRPT_ERR_ARG;
+	}
+	if (p->kernel == LRPT_KERNEL_SPEC) {
+		if (spec_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
+		h->kernel = LRPT_KERNEL_SPEC;
+	} else if (p->kernel != LRPT_KERNEL_SIMPLE && ws_supported(h->c)) {
 		if (ws_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
 		h->kernel = LRPT_KERNEL_WS;
 	}
@@ -165,7 +175,7 @@ extern "C" void lrpt_destroy(lrpt_demod_t *h)
 	cudaSetDevice(h->p.device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_init); cudaFree(h->d_snap); cudaFree(h->d_snap_hist); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off);
+	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_init); cudaFree(h->d_snap); cudaFree(h->d_snap_hist); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off); cudaFree(h->d_fallbacks);
 	cudaFree(h->d_raw[0]); cudaFree(h->d_raw[1]); cudaFree(h->d_soft); cudaFree(h->d_symf);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	if (h->h_state) cudaFreeHost(h->h_state);
@@ -202,7 +212,11 @@ static int launch(lrpt_demod *h, LaunchArgs &a, cudaStream_t st)
 {
 	a.c = &h->c; a.d_taps = h->d_taps; a.d_states = h->d_states; a.d_hist = h->d_hist;
 	cudaError_t e;
-	if (h->kernel == LRPT_KERNEL_WS) {
+	if (h->kernel == LRPT_KERNEL_SPEC) {
+		int n = 0;
+		e = launch_spec(a, st, &n, h->d_fallbacks);
+		h->launches += (unsigned long long)n;
+	} else if (h->kernel == LRPT_KERNEL_WS) {
 		int n = 0;
 		e = launch_ws(a, st, &n);
 		h->launches += (unsigned long long)n;
@@ -512,5 +526,15 @@ extern "C" unsigned long long lrpt_launch_count(const lrpt_demod_t *h) { return 
 
 extern "C" const char *lrpt_kernel_name(const lrpt_demod_t *h)
 {
-	return !h ? "" : h->kernel == LRPT_KERNEL_WS ? "ws" : "simple";
+	return !h ? "" : h->kernel == LRPT_KERNEL_WS ? "ws" : h->kernel == LRPT_KERNEL_SPEC ? "spec" : "simple";
+}
+
+extern "C" unsigned long long lrpt_fir_fallbacks(lrpt_demod_t *h)
+{
+	unsigned long long v = 0;
+	if (!h) return 0;
+	cudaSetDevice(h->p.device);
+	cudaDeviceSynchronize();
+	cudaMemcpy(&v, h->d_fallbacks, sizeof(v), cudaMemcpyDeviceToHost);
+	return v;
 }

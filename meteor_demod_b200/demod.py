@@ -246,5 +246,8 @@ class Demod:
     def launch_count(self):
         return int(self.lib.lrpt_launch_count(self.h))
 
+    def fir_fallbacks(self):
+        return int(self.lib.lrpt_fir_fallbacks(self.h))
+
     def kernel_name(self):
         return self.lib.lrpt_kernel_name(self.h).decode()

@@ -19,8 +19,9 @@ def run(B, N, kernel="ws", order=32, L=5, oqpsk=0, symrate=72000, bps=16, reps=3
             ts.append(e0.elapsed_time(e1))
     c = d.counts()
     ms = min(ts)
-    print("kernel=%s B=%d N=%d order=%d L=%d oqpsk=%d: %.2f ms -> %.1f MS/s (%.2f MS/s/stream) nsym[0]=%d locked=%d" % (
-        kernel, B, N, order, L, oqpsk, ms, B*N/ms/1e3, N/ms/1e3, c[0], d.status(0)["locked"]), flush=True)
+    fb = d.fir_fallbacks() / max(1, reps)
+    print("kernel=%s B=%d N=%d order=%d L=%d oqpsk=%d: %.2f ms -> %.1f MS/s (%.2f MS/s/stream) nsym[0]=%d locked=%d fir_fallbacks/run=%.0f (%.3f%% of symbols)" % (
+        kernel, B, N, order, L, oqpsk, ms, B*N/ms/1e3, N/ms/1e3, c[0], d.status(0)["locked"], fb, 100.0*fb/max(1, int(c.sum()))), flush=True)
     d.close()
 
 if __name__ == "__main__":
@@ -28,10 +29,12 @@ if __name__ == "__main__":
     per = synth.baseband(230000, periodic=True).astype(np.complex64)
     print("period gen %.1fs" % (time.time()-t), flush=True)
     import sys as _s
+    kernels = [k for k in ("ws", "spec", "simple") if ("--" + k) in _s.argv] or ["ws"]
     cfgs = ((1, 1<<18), (2048, 1<<18), (4736, 1<<18))
-    for B, N in cfgs:
-        run(B, N, "ws", period=per)
-    if "--all" in _s.argv:
-        run(4736, 1<<17, "ws", order=64, L=8, period=per)
-        per80 = synth.baseband(230000, symrate=80000, oqpsk=True, periodic=True).astype(np.complex64)
-        run(4736, 1<<17, "ws", oqpsk=1, symrate=80000, bps=8, period=per80)
+    for kern in kernels:
+        for B, N in cfgs:
+            run(B, N, kern, period=per)
+        if "--all" in _s.argv:
+            run(4736, 1<<17, kern, order=64, L=8, period=per)
+            per80 = synth.baseband(230000, symrate=80000, oqpsk=True, periodic=True).astype(np.complex64)
+            run(4736, 1<<17, kern, oqpsk=1, symrate=80000, bps=8, period=per80)
