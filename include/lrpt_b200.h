@@ -49,7 +49,7 @@ enum {
 
 /* Which kernel runs the recurrence. AUTO picks the warp-specialised kernel when the
  * configuration fits it and the simple one otherwise; results are bit-identical. */
-enum { LRPT_KERNEL_AUTO = 0, LRPT_KERNEL_SIMPLE = 1, LRPT_KERNEL_WS = 2, LRPT_KERNEL_SPEC = 3 };
+enum { LRPT_KERNEL_AUTO = 0, LRPT_KERNEL_SIMPLE = 1, LRPT_KERNEL_WS = 2, LRPT_KERNEL_SPEC = 3, LRPT_KERNEL_LANE = 4 };
 
 typedef struct lrpt_demod lrpt_demod_t;       /* opaque; owns device buffers + a CUDA stream */
 

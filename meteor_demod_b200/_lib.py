@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("LRPT_SO") or os.path.join(HERE, "liblrpt_b200.so")   # LRPT_SO: A/B builds while tuning
 
 LRPT_OK, LRPT_ERR_ARG, LRPT_ERR_CUDA, LRPT_ERR_NOMEM, LRPT_ERR_CAP, LRPT_ERR_STATE = 0, -1, -2, -3, -4, -5
-KERNELS = {"auto": 0, "simple": 1, "ws": 2, "spec": 3}
+KERNELS = {"auto": 0, "simple": 1, "ws": 2, "spec": 3, "lane": 4}
 
 
 class Params(C.Structure):

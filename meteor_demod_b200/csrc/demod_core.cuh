@@ -352,4 +352,90 @@ LRPT_DEV bool symbol_fast(Loop &r, const lrpt_consts_t &c, const float *lut, int
 	return !bad;
 }
 
+/* ----------------------------------------------------- fast path, pipelined ----
+ *
+ * The Costas NCO phase changes only inside a symbol step, so the oscillator values the NEXT
+ * step will use (fast_sin/fast_cos of -p_phase, pll.c:53-54) are known as soon as this step
+ * has written p_phase. symbol_fast_osc takes them as an input and computes the next pair at
+ * its end, where the work overlaps the tail of the PLL update instead of heading the
+ * dependency chain of the next symbol. Same values, same proof conditions as symbol_fast.
+ */
+struct Osc { float s, co; bool bad; };
+
+LRPT_DEV Osc osc_for(float p_phase)
+{
+	Osc o; o.bad = false;
+	const float nph = -p_phase;
+	o.s = sincos_poly(turn_fraction_fast(nph, o.bad));
+	o.co = sincos_poly(turn_fraction_fast(__double2float_rn(__dadd_rn((double)nph, kHalfPiD)), o.bad));
+	return o;
+}
+
+template <bool OQ>
+LRPT_DEV bool symbol_fast_osc(Loop &r, const lrpt_consts_t &c, const float *lut, int half,
+                              float re, float im, const Osc &osc, float &out_re, float &out_im,
+                              bool &emitted, Osc &next)
+{
+	bool bad = osc.bad;
+	const float s = osc.s, co = osc.co;
+
+	/* agc_apply (agc.c:13-25) */
+	const float keep = 1.0f - 0.001f;
+	r.bias_re = __fadd_rn(__fmul_rn(r.bias_re, keep), __fmul_rn(0.001f, re));
+	r.bias_im = __fadd_rn(__fmul_rn(r.bias_im, keep), __fmul_rn(0.001f, im));
+	const float sr = __fmul_rn(__fsub_rn(re, r.bias_re), r.gain);
+	const float si = __fmul_rn(__fsub_rn(im, r.bias_im), r.gain);
+	const double da = (double)sr, db = (double)si;
+	const float mag = sqrt_to_float_fast(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)), bad);
+	const float g = __fadd_rn(r.gain, __fmul_rn(0.0001f, __fsub_rn(190.0f, mag)));
+	r.gain = (0.0f > g) ? 0.0f : g;
+
+	/* NCO advance (pll.c:61-62), wrap by select */
+	const float p1 = __fadd_rn(r.p_phase, r.p_freq);
+	const float pw = __double2float_rn(__dsub_rn((double)p1, kTwoPiD));
+	const float p2 = (p1 >= kTwoPiF) ? pw : p1;
+
+	if (OQ && half == 1) {                                  /* demod.c:66-71: I arm only */
+		r.oq_inphase = __fsub_rn(__fmul_rn(sr, co), __fmul_rn(si, s));
+		r.p_phase = p2;
+		emitted = false;
+		next = osc_for(p2);
+		return !bad;
+	}
+	if (OQ) {                                               /* demod.c:72-83 */
+		out_im = __fadd_rn(__fmul_rn(sr, s), __fmul_rn(si, co));
+		out_re = r.oq_inphase;
+	} else {                                                /* pll_mix, pll.c:60 */
+		out_re = __fsub_rn(__fmul_rn(sr, co), __fmul_rn(si, s));
+		out_im = __fadd_rn(__fmul_rn(sr, s), __fmul_rn(si, co));
+	}
+
+	/* phase first: the next oscillator pair hangs off it */
+	const float error = __fsub_rn(__fmul_rn(lut_tanh(lut, out_re), out_im), __fmul_rn(lut_tanh(lut, out_im), out_re));
+	const float ph = __fadd_rn(p2, __fmul_rn(c.p_alpha, error));
+	bad |= !(fabsf(ph) < kTwoPiF);                          /* else fmod really reduces */
+	r.p_phase = ph;
+	next = osc_for(ph);
+
+	retime(r, c, out_im);                                   /* timing.c:60-95, already branch-free */
+
+	/* rest of pll_update_estimate (pll.c:100-130) */
+	const float f1 = __fadd_rn(r.p_freq, __fmul_rn(c.p_beta, error));
+	r.p_err = __double2float_rn(__dadd_rn((double)__fmul_rn(r.p_err, 1.0f - 0.001f),
+	                                      __dmul_rn(fabs((double)error), (double)0.001f)));
+	const int was = r.locked;
+	const int acquire = (r.p_err < 85.0f && !was) ? 1 : 0;
+	const int now = acquire ? 1 : ((r.p_err > 105.0f && was) ? 0 : was);
+	r.locked = now;
+	r.locked_once |= acquire;
+	const float fsw = __double2float_rn(__dadd_rn((double)f1, r.updown > 0 ? 0.000001 : -0.000001));
+	const float f2 = now ? f1 : fsw;
+	const int up1 = (f2 <= -c.p_fmax) ? 1 : r.updown;
+	r.updown = (f2 >= c.p_fmax) ? -1 : up1;
+	const float f3 = (c.p_fmax < f2) ? c.p_fmax : f2;
+	r.p_freq = (-c.p_fmax > f3) ? -c.p_fmax : f3;
+	emitted = true;
+	return !bad;
+}
+
 } // namespace lrpt

@@ -1,0 +1,433 @@
+/*
+ * demod_lane.cu -- "one lane, one stream, lazily": the throughput kernel for large batches.
+ *
+ * Every warp is the same: lane = stream. A lane keeps the raw samples its delay line needs
+ * (the last taps-1 samples plus the tile in flight, filter.c:39-43) in shared memory IN THE
+ * INPUT'S OWN TYPE (4 bytes per 16-bit I/Q sample, 2 per 8-bit, 8 per float), runs the exact
+ * symbol-rate recurrence (demod_core.cuh) and, at every timing crossing, evaluates the ONE
+ * polyphase output the reference evaluates (filter_get, filter.c:46-65) -- as the reference's
+ * own in-order mul-then-add chain over the taps. No FIR output is computed that the timing
+ * loop does not pick, so the arithmetic per symbol is the reference's: ~4*taps flops of FIR
+ * plus the loop, against 16x (demod_ws.cu, all phases) or 3x + prediction (demod_spec.cu).
+ *
+ * What makes it fast is not a lane's latency (the FIR chain now heads each symbol's dependency
+ * chain) but how many lanes fit: the raw-typed delay line is 0.5-0.8 KB per stream, so one SM
+ * holds 8-16 warps = 256-512 streams whose chains hide each other; there are no producer
+ * warps, no mbarriers and no prediction. demod_spec.cu stays the better kernel below roughly
+ * 40 streams per SM, where one lane's latency is what is measured.
+ *
+ * Shared-memory layout: per warp a window of NE entries x 32 lanes, entry-major
+ * (element of lane l, entry e at [e*32 + l]), so every lane always hits its own bank whatever
+ * its timing phase is. The window is linear: sample m of epoch E sits at entry m - E.start + H;
+ * when it is full the last H entries move to the front (once every NT tiles), which keeps the
+ * tap loop free of index arithmetic (immediate offsets only).
+ *
+ * Global traffic: each lane reads its own row 16 bytes at a time, one tile (LN_T samples)
+ * ahead of use, and writes its int8 symbols; whole 32-byte sectors are consumed, nothing is
+ * read twice.
+ */
+#include <algorithm>
+#include "ws_common.cuh"
+#include "kernels.h"
+
+namespace lrpt {
+
+constexpr int LN_T         = 16;   /* samples per tile (per lane)                          */
+constexpr int LN_MAX_WARPS = 16;   /* warps per CTA = 512 streams                          */
+constexpr int LN_MAX_TAPS  = 1025;
+constexpr int LN_MAX_L     = 8;
+constexpr int LN_LP        = 8;    /* floats per row of the transposed tap table [taps][LN_LP] */
+
+#ifndef LRPT_LANE_CVT
+#define LRPT_LANE_CVT 1            /* 0: integer->float conversion instructions, 1: exponent-splice + subtract */
+#endif
+
+struct LaneArgs {
+	const float  *taps;
+	lrpt_state_t *states;
+	float2       *hist;
+	const uint8_t *raw; size_t raw_stride;
+	int           nsamples;
+	int8_t       *soft; size_t soft_stride;
+	float        *symf; size_t symf_stride;
+	uint32_t     *symq; size_t symq_stride; uint32_t q_base;
+	unsigned      cap;
+	uint32_t     *nsym_out, *out_off;
+	int           first_stream, nstreams;
+	int           W;           /* warps per CTA */
+	int           NT;          /* tiles per window epoch */
+	int           nco_n0;
+	int           div_magic;   /* (x*div_magic) >> 16 == x / interp for 0 <= x < LN_T*interp */
+};
+
+/* ------------------------------------------------------- raw sample formats -- */
+
+/* wavfile.c:58-69 per input type. `elem` is what the window holds; cvt() yields exactly the
+ * float pair wav_read produces. */
+template <int BPS> struct RawT;
+
+template <> struct RawT<16> {
+	typedef uint32_t elem;                       /* I in the low half, Q in the high half */
+	static constexpr int NV = LN_T*4/16;         /* 16-byte vectors per tile and lane     */
+#if LRPT_LANE_CVT
+	/* halves are stored biased (s + 32768, an unsigned 16-bit number); spliced under the exponent
+	 * of 2^23 they read 8388608 + s + 32768 exactly, and the subtraction is exact too */
+	LRPT_DEV static elem prep(uint32_t w) { return w ^ 0x80008000u; }
+	LRPT_DEV static float2 cvt(elem e)
+	{
+		const float i = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7610));
+		const float q = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7632));
+		return make_float2(__fsub_rn(i, 8421376.0f), __fsub_rn(q, 8421376.0f));
+	}
+#else
+	LRPT_DEV static elem prep(uint32_t w) { return w; }
+	LRPT_DEV static float2 cvt(elem e)
+	{
+		return make_float2((float)(short)(e & 0xffffu), (float)(short)(e >> 16));
+	}
+#endif
+	LRPT_DEV static elem from_float(float2 v)
+	{
+		const uint32_t i = (uint32_t)(int)v.x & 0xffffu, q = (uint32_t)(int)v.y & 0xffffu;
+		return prep(i | (q << 16));
+	}
+	/* vector j of a tile -> its 4 elements */
+	LRPT_DEV static void unpack(const uint4 &v, elem (&e)[16/sizeof(elem)])
+	{
+		e[0] = prep(v.x); e[1] = prep(v.y); e[2] = prep(v.z); e[3] = prep(v.w);
+	}
+	LRPT_DEV static elem load1(const uint8_t *row, int idx) { return prep(reinterpret_cast<const uint32_t *>(row)[idx]); }
+	LRPT_DEV static elem zero() { return prep(0u); }
+};
+
+template <> struct RawT<8> {
+	typedef uint16_t elem;                       /* I low byte, Q high byte, both offset-128 (wavfile.c:59-61) */
+	static constexpr int NV = LN_T*2/16;
+	LRPT_DEV static float2 cvt(elem e)
+	{
+		const uint32_t w = e;
+		const float i = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440));
+		const float q = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441));
+		return make_float2(__fsub_rn(i, 8388736.0f), __fsub_rn(q, 8388736.0f));
+	}
+	LRPT_DEV static elem from_float(float2 v)
+	{
+		return (elem)((((int)v.x + 128) & 0xff) | ((((int)v.y + 128) & 0xff) << 8));
+	}
+	LRPT_DEV static void unpack(const uint4 &v, elem (&e)[16/sizeof(elem)])
+	{
+		e[0] = (elem)(v.x & 0xffffu); e[1] = (elem)(v.x >> 16); e[2] = (elem)(v.y & 0xffffu); e[3] = (elem)(v.y >> 16);
+		e[4] = (elem)(v.z & 0xffffu); e[5] = (elem)(v.z >> 16); e[6] = (elem)(v.w & 0xffffu); e[7] = (elem)(v.w >> 16);
+	}
+	LRPT_DEV static elem load1(const uint8_t *row, int idx) { return reinterpret_cast<const uint16_t *>(row)[idx]; }
+	LRPT_DEV static elem zero() { return (elem)0x8080u; }
+};
+
+template <> struct RawT<32> {
+	typedef float2 elem;
+	static constexpr int NV = LN_T*8/16;
+	LRPT_DEV static float2 cvt(elem e) { return e; }
+	LRPT_DEV static elem from_float(float2 v) { return v; }
+	LRPT_DEV static void unpack(const uint4 &v, elem (&e)[16/sizeof(elem)])
+	{
+		e[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+		e[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+	}
+	LRPT_DEV static elem load1(const uint8_t *row, int idx) { return reinterpret_cast<const float2 *>(row)[idx]; }
+	LRPT_DEV static elem zero() { return make_float2(0.f, 0.f); }
+};
+
+/* One FULL tile (LN_T samples starting at s0) of a lane's row into registers. */
+template <int BPS>
+LRPT_DEV void tile_load(const uint8_t *row, int s0, uint4 (&pf)[RawT<BPS>::NV])
+{
+	typedef RawT<BPS> R;
+	const uint4 *src = reinterpret_cast<const uint4 *>(row + (size_t)s0*sizeof(typename R::elem));
+#pragma unroll
+	for (int j = 0; j < R::NV; j++) pf[j] = __ldg(src + j);
+}
+
+/* The last, partial tile goes from global memory to the window element by element. */
+template <int BPS>
+LRPT_DEV void tile_copy_partial(typename RawT<BPS>::elem *col, int e0, const uint8_t *row, int s0, int nsamples)
+{
+	typedef RawT<BPS> R;
+#pragma unroll 1
+	for (int i = 0; i < LN_T; i++)
+		col[(e0 + i)*32] = (s0 + i < nsamples) ? R::load1(row, s0 + i) : R::zero();
+}
+
+/* Registers -> window entries [e0, e0+LN_T) of this lane's column. */
+template <int BPS>
+LRPT_DEV void tile_store(typename RawT<BPS>::elem *col, int e0, const uint4 (&pf)[RawT<BPS>::NV])
+{
+	typedef RawT<BPS> R;
+	constexpr int PER = 16/sizeof(typename R::elem);
+#pragma unroll
+	for (int j = 0; j < R::NV; j++) {
+		typename R::elem e[PER];
+		R::unpack(pf[j], e);
+#pragma unroll
+		for (int i = 0; i < PER; i++) col[(e0 + j*PER + i)*32] = e[i];
+	}
+}
+
+/* filter_get(flt, i), filter.c:46-65: w = this lane's column at the entry of the oldest sample,
+ * hb = taps table at this lane's bank (row stride LP). acc = acc + x*h, oldest first, multiply
+ * and add rounded separately. */
+template <int BPS, int LP>
+LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb, int taps)
+{
+	typedef RawT<BPS> R;
+	float ar = 0.0f, ai = 0.0f;
+	int k = 0;
+#pragma unroll 1
+	for (; k + 8 <= taps; k += 8) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const float2 x = R::cvt(w[(k + j)*32]);
+			const float h = hb[(k + j)*LP];
+			ar = __fadd_rn(ar, __fmul_rn(x.x, h));
+			ai = __fadd_rn(ai, __fmul_rn(x.y, h));
+		}
+	}
+#pragma unroll 1
+	for (; k < taps; k++) {
+		const float2 x = R::cvt(w[k*32]);
+		const float h = hb[k*LP];
+		ar = __fadd_rn(ar, __fmul_rn(x.x, h));
+		ai = __fadd_rn(ai, __fmul_rn(x.y, h));
+	}
+	return make_float2(ar, ai);
+}
+
+/* ------------------------------------------------------------- kernel ------ */
+
+template <bool OQ, int BPS>
+__global__ void __launch_bounds__(32*LN_MAX_WARPS, 1)
+demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
+{
+	typedef RawT<BPS> R;
+	typedef typename R::elem elem;
+	constexpr int LP = LN_LP;
+	constexpr int T = LN_T;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+
+	const int taps = c.taps, H = taps - 1, L = c.interp;
+	const int NT = a.NT;
+	const int NE = H + NT*T;                                        /* window entries */
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	float *lut = reinterpret_cast<float *>(smem_raw);               /* [32] */
+	float *hT  = lut + 32;                                          /* [taps][LP] */
+	elem *wins = reinterpret_cast<elem *>(hT + ((taps*LP + 3) & ~3));   /* [W][NE][32] */
+
+	if (threadIdx.x < 32) lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
+	for (int i = threadIdx.x; i < taps*LP; i += blockDim.x) {
+		const int k = i/LP, p = i - k*LP;
+		hT[i] = (p < L) ? a.taps[p*taps + k] : 0.0f;
+	}
+	__syncthreads();
+
+	const int local = (blockIdx.x*a.W + warp)*32 + lane;            /* launch-local stream index */
+	if ((blockIdx.x*a.W + warp)*32 >= a.nstreams) return;           /* whole warp without streams */
+	const bool active = local < a.nstreams;
+	const int lrow = active ? local : a.nstreams - 1;               /* idle lanes shadow a valid row (loads only) */
+	const int sid = a.first_stream + local;
+	const uint8_t *row = a.raw + (size_t)lrow*a.raw_stride;
+	elem *col = wins + (size_t)warp*NE*32 + lane;
+
+	Loop r;
+	long long nsymbols = 0, first_lock = -1;
+	unsigned off = 0, nsym = 0;
+	char2 *out = nullptr; float2 *outf = nullptr; uint32_t *outq = nullptr;
+	loop_load(r, a.states[a.first_stream + lrow]);
+	if (active) {
+		nsymbols = a.states[sid].nsymbols;
+		first_lock = a.states[sid].first_lock_symbol;
+		off = a.out_off ? a.out_off[local] : 0u;
+		out = reinterpret_cast<char2 *>(a.soft + (size_t)local*a.soft_stride);
+		if (a.symf) outf = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.symf) + (size_t)local*a.symf_stride);
+		if (a.symq) outq = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.symq) + (size_t)local*a.symq_stride);
+	}
+
+	/* prologue: delay line (taps-1 samples, oldest first) at entries [0,H), tile 0 behind it */
+	{
+		const float2 *hs = a.hist + (size_t)(a.first_stream + lrow)*H;
+		for (int j = 0; j < H; j++) col[j*32] = R::from_float(hs[j]);
+	}
+	uint4 pf[R::NV];
+	if (T <= a.nsamples) tile_load<BPS>(row, 0, pf);
+
+	const int ntiles = (a.nsamples + T - 1)/T;
+	const int Qend = a.nsamples*L;
+	int Q = 0;
+	bool have_x = false; int Qx = 0, half = 0;
+	Osc osc = osc_for(r.p_phase);
+	int ep0 = 0;                                                    /* first sample of the window epoch */
+
+	for (int t = 0; t < ntiles; t++) {
+		/* append tile t; start the loads of tile t+1 */
+		const int te = t - (ep0/T);
+		if ((t + 1)*T <= a.nsamples) tile_store<BPS>(col, H + te*T, pf);
+		else tile_copy_partial<BPS>(col, H + te*T, row, t*T, a.nsamples);
+		if ((t + 2)*T <= a.nsamples) tile_load<BPS>(row, (t + 1)*T, pf);
+		__syncwarp();
+
+		const int q0 = t*T*L;
+		const int q1 = min((t + 1)*T, a.nsamples)*L;
+		/* Warp-uniform rounds, so that the lanes (streams) stay converged: in each round every
+		 * lane that still owes this tile a crossing runs its NCO search, then every lane holding
+		 * a crossing inside the tile takes its FIR + symbol step, all together. */
+		while (true) {
+			if (active && !have_x && Q < q1)
+				have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
+			__syncwarp();
+			const bool ready = active && have_x && Qx < q1;
+			if (!__any_sync(0xffffffffu, ready)) break;
+			if (ready) {
+				/* filter_get(flt, i) at sub-step Qx = n*L + i (demod.c:33-35) */
+				const int dq = Qx - q0;
+				const int nr = (dq*a.div_magic) >> 16, i = dq - nr*L;       /* sample within the tile, sub-step */
+				const float2 y = fir_lazy<BPS, LP>(col + (te*T + nr)*32, hT + (L - 1 - i), taps);
+				const int Qsym = Qx;
+				const Loop saved = r;
+				float ore, oim; bool emitted; Osc next;
+				if (!symbol_fast_osc<OQ>(r, c, lut, half, y.x, y.y, osc, ore, oim, emitted, next)) {
+					r = saved;                                       /* a shortcut was not provably exact */
+					emitted = symbol_event(r, c, lut, half, y.x, y.y, ore, oim);
+					next = osc_for(r.p_phase);
+				}
+				osc = next;
+				if (emitted) {
+					if (r.locked_once && first_lock < 0) first_lock = nsymbols;
+					if (off + nsym < a.cap) {
+						out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
+						if (outf) outf[off + nsym] = make_float2(ore, oim);
+						if (outq) outq[off + nsym] = a.q_base + (uint32_t)Qsym;
+					}
+					nsym++; nsymbols++;
+				}
+				have_x = false;
+			}
+			__syncwarp();
+		}
+
+		/* window full: the last H samples become the head of the next epoch */
+		if (te + 1 == NT && t + 1 < ntiles) {
+			for (int j = 0; j < H; j++) col[j*32] = col[(NT*T + j)*32];
+			ep0 += NT*T;
+		}
+	}
+
+	/* epilogue: the last taps-1 samples are the next call's delay line */
+	if (active) {
+		float2 *hs = a.hist + (size_t)sid*H;
+		for (int j = 0; j < H; j++) {
+			const int m = a.nsamples - H + j;                       /* may be negative: still in the old history */
+			hs[j] = R::cvt(col[(m - ep0 + H)*32]);
+		}
+		loop_store(r, a.states[sid]);
+		a.states[sid].nsamples += a.nsamples;
+		a.states[sid].nsymbols = nsymbols;
+		a.states[sid].first_lock_symbol = first_lock;
+		if (a.nsym_out) a.nsym_out[local] = nsym;
+		if (a.out_off) a.out_off[local] = off + nsym;
+	}
+}
+
+/* ------------------------------------------------------------- host side --- */
+
+static int ln_num_sms = 0, ln_max_smem = 0;
+
+static size_t ln_fixed_smem(int taps)
+{
+	return 32*sizeof(float) + (size_t)((taps*LN_LP + 3) & ~3)*sizeof(float);
+}
+
+static size_t ln_warp_smem(int taps, int NT, int bps) { return (size_t)((taps - 1) + NT*LN_T)*32*(size_t)(bps/4); }
+
+bool lane_supported(const lrpt_consts_t &c)
+{
+	return c.interp >= 1 && c.interp <= LN_MAX_L && c.taps >= 1 && c.taps <= LN_MAX_TAPS &&
+	       (c.bps == 8 || c.bps == 16 || c.bps == 32);
+}
+
+template <bool OQ, int BPS> static cudaError_t ln_attr1()
+{
+	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+}
+
+cudaError_t lane_prepare(int device)
+{
+	cudaError_t e;
+	if ((e = cudaDeviceGetAttribute(&ln_num_sms, cudaDevAttrMultiProcessorCount, device))) return e;
+	if ((e = cudaDeviceGetAttribute(&ln_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device))) return e;
+	if ((e = ln_attr1<false, 8>()) || (e = ln_attr1<false, 16>()) || (e = ln_attr1<false, 32>()) ||
+	    (e = ln_attr1<true, 8>()) || (e = ln_attr1<true, 16>()) || (e = ln_attr1<true, 32>())) return e;
+	return cudaSuccess;
+}
+
+template <bool OQ> static void ln_launch1(const lrpt_consts_t &c, const LaneArgs &w, int blocks, size_t smem, cudaStream_t st)
+{
+	const int threads = 32*w.W;
+	if (c.bps == 16)     demod_lane_kernel<OQ, 16><<<blocks, threads, smem, st>>>(c, w);
+	else if (c.bps == 8) demod_lane_kernel<OQ, 8><<<blocks, threads, smem, st>>>(c, w);
+	else                 demod_lane_kernel<OQ, 32><<<blocks, threads, smem, st>>>(c, w);
+}
+
+cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
+{
+	const lrpt_consts_t &c = *a.c;
+	const int L = c.interp, taps = c.taps;
+	const size_t fixed = ln_fixed_smem(taps);
+	/* warps per CTA: spread the batch over every SM first, then stack warps (one CTA per SM) */
+	const int nwarps = (a.nstreams + 31)/32;
+	int W = std::max(1, std::min((nwarps + ln_num_sms - 1)/ln_num_sms, LN_MAX_WARPS));
+	/* window epoch length: as long as shared memory allows (amortises the epoch move), at least
+	 * long enough that the moved head and tail do not overlap */
+	const int nt_min = std::max(1, (taps - 1 + LN_T - 1)/LN_T);
+	while (W > 1 && fixed + W*ln_warp_smem(taps, nt_min, c.bps) > (size_t)ln_max_smem) W--;
+	if (fixed + W*ln_warp_smem(taps, nt_min, c.bps) > (size_t)ln_max_smem) return cudaErrorInvalidConfiguration;
+	int NT = nt_min;
+	while (NT < 4*nt_min && NT < 64 && fixed + W*ln_warp_smem(taps, NT + 1, c.bps) <= (size_t)ln_max_smem) NT++;
+	/* level the waves when shared memory caps W */
+	const int per_wave = ln_num_sms*W;
+	const int waves = (nwarps + per_wave - 1)/per_wave;
+	W = std::max(1, std::min(W, (nwarps + waves*ln_num_sms - 1)/(waves*ln_num_sms)));
+	const int blocks = (nwarps + W - 1)/W;
+	const size_t smem = fixed + W*ln_warp_smem(taps, NT, c.bps);
+
+	int n = 0;
+	size_t done = 0;
+	while (done < a.nsamples) {
+		const size_t ns = std::min(a.nsamples - done, (size_t)WS_MAX_SAMPLES);
+		if (done && !a.d_out_off) return cudaErrorInvalidValue;
+		LaneArgs w;
+		w.taps = a.d_taps; w.states = a.d_states; w.hist = a.d_hist;
+		w.raw = reinterpret_cast<const uint8_t *>(a.d_raw) + done*(size_t)(c.bps/4); w.raw_stride = a.raw_stride;
+		w.nsamples = (int)ns;
+		w.soft = a.d_soft; w.soft_stride = a.soft_stride; w.symf = a.d_symf; w.symf_stride = a.symf_stride;
+		w.symq = a.d_symq; w.symq_stride = a.symq_stride; w.q_base = (uint32_t)(done*(size_t)L);
+		w.cap = a.cap; w.nsym_out = a.d_nsym; w.out_off = a.d_out_off;
+		w.first_stream = a.first_stream; w.nstreams = a.nstreams; w.W = W; w.NT = NT;
+		{
+			const double nominal = (c.oqpsk ? 3.14159265358979 : 6.28318530717959)/(double)c.t_center;
+			const int cmin = (int)nominal - 1;
+			w.nco_n0 = cmin > 1 ? 4*((cmin - 1)/4) : 0;
+		}
+		w.div_magic = (65536 + L - 1)/L;
+		for (int x = 0; x < LN_T*L; x++)
+			if (((x*w.div_magic) >> 16) != x/L) return cudaErrorInvalidConfiguration;
+		if (c.oqpsk) ln_launch1<true>(c, w, blocks, smem, st);
+		else         ln_launch1<false>(c, w, blocks, smem, st);
+		n++;
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { if (launches) *launches = n; return e; }
+		done += ns;
+	}
+	if (launches) *launches = n;
+	return cudaSuccess;
+}
+
+} // namespace lrpt

@@ -42,4 +42,9 @@ bool        spec_supported(const lrpt_consts_t &c);
 cudaError_t spec_prepare(int device);
 cudaError_t launch_spec(const LaunchArgs &a, cudaStream_t st, int *launches, unsigned long long *d_fallbacks);
 
+/* lane-per-stream lazy-FIR kernel (demod_lane.cu) */
+bool        lane_supported(const lrpt_consts_t &c);
+cudaError_t lane_prepare(int device);
+cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches);
+
 } // namespace lrpt

@@ -156,7 +156,14 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 		fprintf(stderr, "lrpt_create: configuration not supported by the speculative-FIR kernel\n");
 		lrpt_destroy(h); return LRPT_ERR_ARG;
 	}
-	if (p->kernel == LRPT_KERNEL_SPEC) {
+	if (p->kernel == LRPT_KERNEL_LANE && !lane_supported(h->c)) {
+		fprintf(stderr, "lrpt_create: configuration not supported by the lane kernel\n");
+		lrpt_destroy(h); return LRPT_ERR_ARG;
+	}
+	if (p->kernel == LRPT_KERNEL_LANE) {
+		if (lane_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
+		h->kernel = LRPT_KERNEL_LANE;
+	} else if (p->kernel == LRPT_KERNEL_SPEC) {
 		if (spec_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
 		h->kernel = LRPT_KERNEL_SPEC;
 	} else if (p->kernel != LRPT_KERNEL_SIMPLE && ws_supported(h->c)) {
@@ -215,6 +222,10 @@ static int launch(lrpt_demod *h, LaunchArgs &a, cudaStream_t st)
 	if (h->kernel == LRPT_KERNEL_SPEC) {
 		int n = 0;
 		e = launch_spec(a, st, &n, h->d_fallbacks);
+		h->launches += (unsigned long long)n;
+	} else if (h->kernel == LRPT_KERNEL_LANE) {
+		int n = 0;
+		e = launch_lane(a, st, &n);
 		h->launches += (unsigned long long)n;
 	} else if (h->kernel == LRPT_KERNEL_WS) {
 		int n = 0;
@@ -526,7 +537,8 @@ extern "C" unsigned long long lrpt_launch_count(const lrpt_demod_t *h) { return 
 
 extern "C" const char *lrpt_kernel_name(const lrpt_demod_t *h)
 {
-	return !h ? "" : h->kernel == LRPT_KERNEL_WS ? "ws" : h->kernel == LRPT_KERNEL_SPEC ? "spec" : "simple";
+	return !h ? "" : h->kernel == LRPT_KERNEL_WS ? "ws" : h->kernel == LRPT_KERNEL_SPEC ? "spec" :
+	       h->kernel == LRPT_KERNEL_LANE ? "lane" : "simple";
 }
 
 extern "C" unsigned long long lrpt_fir_fallbacks(lrpt_demod_t *h)

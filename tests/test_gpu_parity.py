@@ -13,7 +13,7 @@ from conftest import CONFIGS, bits, make_case
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-KERNELS = ["simple", "ws", "spec"]
+KERNELS = ["simple", "ws", "spec", "lane"]
 STATE_KEYS = ("t_phase", "t_freq", "t_prev", "agc_gain", "agc_bias_re", "agc_bias_im", "p_phase", "p_freq", "p_err")
 INT_KEYS = ("p_locked", "p_locked_once", "p_updown", "t_dual_state", "nsamples", "nsymbols", "first_lock_symbol")
 
@@ -24,7 +24,7 @@ def demod_for(cfg, kernel, nstreams=1):
         return Demod(symrate=cfg["symrate"], oqpsk=cfg["oqpsk"], bps=cfg["bps"], rrc_order=cfg["order"],
                      interp_factor=cfg["interp"], nstreams=nstreams, kernel=kernel)
     except LrptError as e:
-        if kernel in ("ws", "spec") and e.code == -1:
+        if kernel in ("ws", "spec", "lane") and e.code == -1:
             pytest.skip("configuration not covered by the %s kernel" % kernel)
         raise
 

@@ -29,8 +29,11 @@ if __name__ == "__main__":
     per = synth.baseband(230000, periodic=True).astype(np.complex64)
     print("period gen %.1fs" % (time.time()-t), flush=True)
     import sys as _s
-    kernels = [k for k in ("ws", "spec", "simple") if ("--" + k) in _s.argv] or ["ws"]
+    kernels = [k for k in ("ws", "spec", "simple", "lane") if ("--" + k) in _s.argv] or ["ws"]
     cfgs = ((1, 1<<18), (2048, 1<<18), (4736, 1<<18))
+    for a_ in _s.argv:
+        if a_.startswith("--cfg="):
+            cfgs = tuple(tuple(int(v) for v in c_.split(":")) for c_ in a_[6:].split(","))
     for kern in kernels:
         for B, N in cfgs:
             run(B, N, kern, period=per)
