@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=4736, help="independent streams per GPU")
-    ap.add_argument("--samples", type=int, default=1 << 19, help="samples per stream per step")
+    ap.add_argument("--streams", type=int, default=75776, help="independent streams per GPU (148 SMs x 16 warps x 32 lanes)")
+    ap.add_argument("--samples", type=int, default=1 << 15, help="samples per stream per step")
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
                     help="batch: independent streams (exact); sharded: ONE stream of --stream-samples per job, "

@@ -47,8 +47,10 @@ enum {
 	LRPT_ERR_STATE = -5    /* state blob does not match this handle's configuration */
 };
 
-/* Which kernel runs the recurrence. AUTO picks the warp-specialised kernel when the
- * configuration fits it and the simple one otherwise; results are bit-identical. */
+/* Which kernel runs the recurrence; results are bit-identical. AUTO picks by streams per SM:
+ * WS (all-phase FIR producers + one recurrence warp) for few streams, SPEC (speculative FIR)
+ * in between, LANE (one lane per stream, lazy FIR, many warps per SM) for large batches;
+ * SIMPLE (one thread per stream, source order) covers whatever the others do not. */
 enum { LRPT_KERNEL_AUTO = 0, LRPT_KERNEL_SIMPLE = 1, LRPT_KERNEL_WS = 2, LRPT_KERNEL_SPEC = 3, LRPT_KERNEL_LANE = 4 };
 
 typedef struct lrpt_demod lrpt_demod_t;       /* opaque; owns device buffers + a CUDA stream */

@@ -27,6 +27,8 @@
  * read twice.
  */
 #include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
 #include "ws_common.cuh"
 #include "kernels.h"
 
@@ -41,6 +43,22 @@ constexpr int LN_LP        = 8;    /* floats per row of the transposed tap table
 #ifndef LRPT_LANE_CVT
 #define LRPT_LANE_CVT 1            /* 0: integer->float conversion instructions, 1: exponent-splice + subtract */
 #endif
+#ifndef LRPT_LANE_PACKED
+#define LRPT_LANE_PACKED 1         /* 1: the I and Q chains as one packed f32x2 chain (sm_100 FMUL2/FFMA2/FADD2) */
+#endif
+
+/* ------------------------------------------------------- packed f32x2 helpers -- *
+ * sm_100 has two-wide fp32 instructions on 64-bit register pairs; each half is an ordinary IEEE
+ * operation, so (re, im) of one tap can share instructions without changing a bit. One trap:
+ * ptxas CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (measured:
+ * tools/mb/f32x2.cu). The accumulate step is therefore written p*one + acc with `one` = 1.0f
+ * arriving as a kernel argument, which ptxas cannot fold: fma(p, 1, acc) = RN(p + acc) exactly. */
+typedef unsigned long long f32x2_t;
+LRPT_DEV f32x2_t pk2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+LRPT_DEV float2 upk2(f32x2_t v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+LRPT_DEV f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+LRPT_DEV f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+LRPT_DEV f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 struct LaneArgs {
 	const float  *taps;
@@ -58,6 +76,7 @@ struct LaneArgs {
 	int           NT;          /* tiles per window epoch */
 	int           nco_n0;
 	int           div_magic;   /* (x*div_magic) >> 16 == x / interp for 0 <= x < LN_T*interp */
+	float         one;         /* 1.0f, opaque to the compiler (see the packed f32x2 helpers) */
 };
 
 /* ------------------------------------------------------- raw sample formats -- */
@@ -79,12 +98,19 @@ template <> struct RawT<16> {
 		const float q = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7632));
 		return make_float2(__fsub_rn(i, 8421376.0f), __fsub_rn(q, 8421376.0f));
 	}
+	LRPT_DEV static f32x2_t cvt2(elem e)
+	{
+		const float i = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7610));
+		const float q = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7632));
+		return add2(pk2(i, q), pk2(-8421376.0f, -8421376.0f));
+	}
 #else
 	LRPT_DEV static elem prep(uint32_t w) { return w; }
 	LRPT_DEV static float2 cvt(elem e)
 	{
 		return make_float2((float)(short)(e & 0xffffu), (float)(short)(e >> 16));
 	}
+	LRPT_DEV static f32x2_t cvt2(elem e) { const float2 v = cvt(e); return pk2(v.x, v.y); }
 #endif
 	LRPT_DEV static elem from_float(float2 v)
 	{
@@ -110,6 +136,13 @@ template <> struct RawT<8> {
 		const float q = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441));
 		return make_float2(__fsub_rn(i, 8388736.0f), __fsub_rn(q, 8388736.0f));
 	}
+	LRPT_DEV static f32x2_t cvt2(elem e)
+	{
+		const uint32_t w = e;
+		const float i = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440));
+		const float q = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441));
+		return add2(pk2(i, q), pk2(-8388736.0f, -8388736.0f));
+	}
 	LRPT_DEV static elem from_float(float2 v)
 	{
 		return (elem)((((int)v.x + 128) & 0xff) | ((((int)v.y + 128) & 0xff) << 8));
@@ -127,6 +160,7 @@ template <> struct RawT<32> {
 	typedef float2 elem;
 	static constexpr int NV = LN_T*8/16;
 	LRPT_DEV static float2 cvt(elem e) { return e; }
+	LRPT_DEV static f32x2_t cvt2(elem e) { return pk2(e.x, e.y); }
 	LRPT_DEV static elem from_float(float2 v) { return v; }
 	LRPT_DEV static void unpack(const uint4 &v, elem (&e)[16/sizeof(elem)])
 	{
@@ -176,9 +210,29 @@ LRPT_DEV void tile_store(typename RawT<BPS>::elem *col, int e0, const uint4 (&pf
  * hb = taps table at this lane's bank (row stride LP). acc = acc + x*h, oldest first, multiply
  * and add rounded separately. */
 template <int BPS, int LP>
-LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb, int taps)
+LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb, int taps, float one)
 {
 	typedef RawT<BPS> R;
+#if LRPT_LANE_PACKED
+	f32x2_t acc = pk2(0.0f, 0.0f);
+	const f32x2_t one2 = pk2(one, one);
+	int k = 0;
+#pragma unroll 1
+	for (; k + 8 <= taps; k += 8) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const float h = hb[(k + j)*LP];
+			acc = fma2(mul2(R::cvt2(w[(k + j)*32]), pk2(h, h)), one2, acc);
+		}
+	}
+#pragma unroll 1
+	for (; k < taps; k++) {
+		const float h = hb[k*LP];
+		acc = fma2(mul2(R::cvt2(w[k*32]), pk2(h, h)), one2, acc);
+	}
+	return upk2(acc);
+#else
+	(void)one;
 	float ar = 0.0f, ai = 0.0f;
 	int k = 0;
 #pragma unroll 1
@@ -199,11 +253,12 @@ LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const f
 		ai = __fadd_rn(ai, __fmul_rn(x.y, h));
 	}
 	return make_float2(ar, ai);
+#endif
 }
 
 /* ------------------------------------------------------------- kernel ------ */
 
-template <bool OQ, int BPS>
+template <bool OQ, int BPS, bool AUX>
 __global__ void __launch_bounds__(32*LN_MAX_WARPS, 1)
 demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 {
@@ -247,8 +302,8 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 		first_lock = a.states[sid].first_lock_symbol;
 		off = a.out_off ? a.out_off[local] : 0u;
 		out = reinterpret_cast<char2 *>(a.soft + (size_t)local*a.soft_stride);
-		if (a.symf) outf = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.symf) + (size_t)local*a.symf_stride);
-		if (a.symq) outq = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.symq) + (size_t)local*a.symq_stride);
+		if (AUX && a.symf) outf = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.symf) + (size_t)local*a.symf_stride);
+		if (AUX && a.symq) outq = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.symq) + (size_t)local*a.symq_stride);
 	}
 
 	/* prologue: delay line (taps-1 samples, oldest first) at entries [0,H), tile 0 behind it */
@@ -263,7 +318,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	const int Qend = a.nsamples*L;
 	int Q = 0;
 	bool have_x = false; int Qx = 0, half = 0;
-	Osc osc = osc_for(r.p_phase);
+	Osc osc = osc_for(r.p_phase);                                   /* fast_sin/fast_cos(-p_phase), pll.c:53-54 */
 	int ep0 = 0;                                                    /* first sample of the window epoch */
 
 	for (int t = 0; t < ntiles; t++) {
@@ -289,8 +344,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				/* filter_get(flt, i) at sub-step Qx = n*L + i (demod.c:33-35) */
 				const int dq = Qx - q0;
 				const int nr = (dq*a.div_magic) >> 16, i = dq - nr*L;       /* sample within the tile, sub-step */
-				const float2 y = fir_lazy<BPS, LP>(col + (te*T + nr)*32, hT + (L - 1 - i), taps);
-				const int Qsym = Qx;
+				const float2 y = fir_lazy<BPS, LP>(col + (te*T + nr)*32, hT + (L - 1 - i), taps, a.one);
 				const Loop saved = r;
 				float ore, oim; bool emitted; Osc next;
 				if (!symbol_fast_osc<OQ>(r, c, lut, half, y.x, y.y, osc, ore, oim, emitted, next)) {
@@ -303,8 +357,8 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 					if (r.locked_once && first_lock < 0) first_lock = nsymbols;
 					if (off + nsym < a.cap) {
 						out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
-						if (outf) outf[off + nsym] = make_float2(ore, oim);
-						if (outq) outq[off + nsym] = a.q_base + (uint32_t)Qsym;
+						if (AUX && outf) outf[off + nsym] = make_float2(ore, oim);
+						if (AUX && outq) outq[off + nsym] = a.q_base + (uint32_t)Qx;
 					}
 					nsym++; nsymbols++;
 				}
@@ -315,6 +369,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 
 		/* window full: the last H samples become the head of the next epoch */
 		if (te + 1 == NT && t + 1 < ntiles) {
+			/* ascending in-place copy towards lower entries: safe when source and destination overlap */
 			for (int j = 0; j < H; j++) col[j*32] = col[(NT*T + j)*32];
 			ep0 += NT*T;
 		}
@@ -355,7 +410,9 @@ bool lane_supported(const lrpt_consts_t &c)
 
 template <bool OQ, int BPS> static cudaError_t ln_attr1()
 {
-	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	cudaError_t e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	if (e) return e;
+	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
 }
 
 cudaError_t lane_prepare(int device)
@@ -371,9 +428,13 @@ cudaError_t lane_prepare(int device)
 template <bool OQ> static void ln_launch1(const lrpt_consts_t &c, const LaneArgs &w, int blocks, size_t smem, cudaStream_t st)
 {
 	const int threads = 32*w.W;
-	if (c.bps == 16)     demod_lane_kernel<OQ, 16><<<blocks, threads, smem, st>>>(c, w);
-	else if (c.bps == 8) demod_lane_kernel<OQ, 8><<<blocks, threads, smem, st>>>(c, w);
-	else                 demod_lane_kernel<OQ, 32><<<blocks, threads, smem, st>>>(c, w);
+	const bool aux = w.symf || w.symq;                              /* optional float / index side outputs */
+#define LN_GO(B) do { if (aux) demod_lane_kernel<OQ, B, true><<<blocks, threads, smem, st>>>(c, w); \
+                      else     demod_lane_kernel<OQ, B, false><<<blocks, threads, smem, st>>>(c, w); } while (0)
+	if (c.bps == 16)     LN_GO(16);
+	else if (c.bps == 8) LN_GO(8);
+	else                 LN_GO(32);
+#undef LN_GO
 }
 
 cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
@@ -381,22 +442,23 @@ cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 	const lrpt_consts_t &c = *a.c;
 	const int L = c.interp, taps = c.taps;
 	const size_t fixed = ln_fixed_smem(taps);
-	/* warps per CTA: spread the batch over every SM first, then stack warps (one CTA per SM) */
+	/* warps per CTA: spread the batch over every SM first, then stack warps (one CTA per SM). The
+	 * window epoch is at least 2 tiles (the head move is an in-place ascending copy, so it may
+	 * overlap its source) and as long as shared memory allows, which amortises that move. */
 	const int nwarps = (a.nstreams + 31)/32;
 	int W = std::max(1, std::min((nwarps + ln_num_sms - 1)/ln_num_sms, LN_MAX_WARPS));
-	/* window epoch length: as long as shared memory allows (amortises the epoch move), at least
-	 * long enough that the moved head and tail do not overlap */
-	const int nt_min = std::max(1, (taps - 1 + LN_T - 1)/LN_T);
-	while (W > 1 && fixed + W*ln_warp_smem(taps, nt_min, c.bps) > (size_t)ln_max_smem) W--;
-	if (fixed + W*ln_warp_smem(taps, nt_min, c.bps) > (size_t)ln_max_smem) return cudaErrorInvalidConfiguration;
-	int NT = nt_min;
-	while (NT < 4*nt_min && NT < 64 && fixed + W*ln_warp_smem(taps, NT + 1, c.bps) <= (size_t)ln_max_smem) NT++;
+	int NT = 2;
+	while (W > 1 && fixed + W*ln_warp_smem(taps, NT, c.bps) > (size_t)ln_max_smem) W--;
+	if (fixed + W*ln_warp_smem(taps, NT, c.bps) > (size_t)ln_max_smem) NT = 1;
+	if (fixed + W*ln_warp_smem(taps, NT, c.bps) > (size_t)ln_max_smem) return cudaErrorInvalidConfiguration;
 	/* level the waves when shared memory caps W */
 	const int per_wave = ln_num_sms*W;
 	const int waves = (nwarps + per_wave - 1)/per_wave;
 	W = std::max(1, std::min(W, (nwarps + waves*ln_num_sms - 1)/(waves*ln_num_sms)));
+	while (NT < 16 && fixed + W*ln_warp_smem(taps, NT + 1, c.bps) <= (size_t)ln_max_smem) NT++;
 	const int blocks = (nwarps + W - 1)/W;
 	const size_t smem = fixed + W*ln_warp_smem(taps, NT, c.bps);
+	if (getenv("LRPT_LANE_DEBUG")) fprintf(stderr, "lane: streams %d W %d NT %d blocks %d smem %zu\n", a.nstreams, W, NT, blocks, smem);
 
 	int n = 0;
 	size_t done = 0;
@@ -416,6 +478,7 @@ cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 			const int cmin = (int)nominal - 1;
 			w.nco_n0 = cmin > 1 ? 4*((cmin - 1)/4) : 0;
 		}
+		w.one = 1.0f;
 		w.div_magic = (65536 + L - 1)/L;
 		for (int x = 0; x < LN_T*L; x++)
 			if (((x*w.div_magic) >> 16) != x/L) return cudaErrorInvalidConfiguration;

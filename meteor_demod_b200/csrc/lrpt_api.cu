@@ -147,29 +147,36 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 	CUC(cudaMallocHost(&h->h_state, sizeof(lrpt_state_t)));
 	CUC(cudaMemcpy(h->d_taps, h->taps.data(), sizeof(float)*h->taps.size(), cudaMemcpyHostToDevice));
 #undef CUC
-	h->kernel = LRPT_KERNEL_SIMPLE;
-	if (p->kernel == LRPT_KERNEL_WS && !ws_supported(h->c)) {
-		fprintf(stderr, "lrpt_create: configuration not supported by the warp-specialised kernel\n");
+	/* Kernel choice. Explicit requests must be supported by that kernel. AUTO goes by streams per SM:
+	 * few streams -> the warp-specialised kernels (shortest time per symbol of one stream: all-phase
+	 * FIR below ~16 streams per SM, speculative FIR up to ~36), many streams -> the lane kernel
+	 * (least work per symbol; needs many warps per SM to hide its latency). All are bit-identical. */
+	int want = p->kernel;
+	if (want == LRPT_KERNEL_AUTO) {
+		int sms = 1;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+		const double per_sm = (double)p->nstreams/(double)(sms > 0 ? sms : 1);
+		if (per_sm > 36.0 && lane_supported(h->c)) want = LRPT_KERNEL_LANE;
+		else if (per_sm > 16.0 && spec_supported(h->c)) want = LRPT_KERNEL_SPEC;
+		else if (ws_supported(h->c)) want = LRPT_KERNEL_WS;
+		else if (lane_supported(h->c)) want = LRPT_KERNEL_LANE;
+		else want = LRPT_KERNEL_SIMPLE;
+	}
+	const bool ok = want == LRPT_KERNEL_SIMPLE || (want == LRPT_KERNEL_WS && ws_supported(h->c)) ||
+	                (want == LRPT_KERNEL_SPEC && spec_supported(h->c)) || (want == LRPT_KERNEL_LANE && lane_supported(h->c));
+	if (!ok) {
+		fprintf(stderr, "lrpt_create: configuration not supported by the requested kernel (%d)\n", want);
 		lrpt_destroy(h); return LRPT_ERR_ARG;
 	}
-	if (p->kernel == LRPT_KERNEL_SPEC && !spec_supported(h->c)) {
-		fprintf(stderr, "lrpt_create: configuration not supported by the speculative-FIR kernel\n");
-		lrpt_destroy(h); return LRPT_ERR_ARG;
+	cudaError_t pe = cudaSuccess;
+	if (want == LRPT_KERNEL_WS) pe = ws_prepare(p->device);
+	else if (want == LRPT_KERNEL_SPEC) pe = spec_prepare(p->device);
+	else if (want == LRPT_KERNEL_LANE) pe = lane_prepare(p->device);
+	if (pe != cudaSuccess) {
+		fprintf(stderr, "lrpt_create: kernel setup: %s\n", cudaGetErrorString(pe));
+		lrpt_destroy(h); return LRPT_ERR_CUDA;
 	}
-	if (p->kernel == LRPT_KERNEL_LANE && !lane_supported(h->c)) {
-		fprintf(stderr, "lrpt_create: configuration not supported by the lane kernel\n");
-		lrpt_destroy(h); return LRPT_ERR_ARG;
-	}
-	if (p->kernel == LRPT_KERNEL_LANE) {
-		if (lane_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
-		h->kernel = LRPT_KERNEL_LANE;
-	} else if (p->kernel == LRPT_KERNEL_SPEC) {
-		if (spec_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
-		h->kernel = LRPT_KERNEL_SPEC;
-	} else if (p->kernel != LRPT_KERNEL_SIMPLE && ws_supported(h->c)) {
-		if (ws_prepare(p->device) != cudaSuccess) { lrpt_destroy(h); return LRPT_ERR_CUDA; }
-		h->kernel = LRPT_KERNEL_WS;
-	}
+	h->kernel = want;
 	rc = upload_initial_state(h);
 	if (rc) { lrpt_destroy(h); return rc; }
 	*out = h;
@@ -318,7 +325,8 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 	 * that the first copy (nothing to overlap with) and the last kernel are short, large enough that a
 	 * launch still runs hundreds of tiles */
 	size_t slab = ((size_t)256 << 20)/(bpsm*(size_t)count);
-	if (slab < 16384) slab = 16384;
+	const size_t slab_min = h->kernel == LRPT_KERNEL_LANE ? 4096 : 16384;   /* lane: short launches cost little */
+	if (slab < slab_min) slab = slab_min;
 	slab = round_up(slab, 4096);
 	if (slab > nsamples) slab = round_up(nsamples ? nsamples : 1, 16);
 	const size_t d_raw_pitch = round_up(slab*bpsm, 256);

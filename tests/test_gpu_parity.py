@@ -173,14 +173,15 @@ def test_edge_inputs(kernel, oracle_mod, lib):
 
 
 def test_configurations_outside_the_fast_kernel_fall_back_exactly(oracle_mod, lib):
-    """interp > 8 or taps > 257 are served by the simple kernel under LRPT_KERNEL_AUTO; asking for the
-    warp-specialised kernel explicitly is refused. Results stay bit-exact."""
+    """taps > 257 are served by the lane kernel and interp > 8 by the simple kernel under LRPT_KERNEL_AUTO;
+    asking for the warp-specialised kernel explicitly is refused. Results stay bit-exact."""
     from meteor_demod_b200 import Demod, LrptError
-    for cfg in (dict(symrate=72000, oqpsk=0, bps=16, order=140, interp=5), dict(symrate=72000, oqpsk=1, bps=8, order=20, interp=11)):
+    for cfg, served_by in ((dict(symrate=72000, oqpsk=0, bps=16, order=140, interp=5), "lane"),
+                           (dict(symrate=72000, oqpsk=1, bps=8, order=20, interp=11), "simple")):
         raw = make_case("C2_oqpsk80k_u8_o32_L5" if cfg["bps"] == 8 else "C1_qpsk72k_s16_o32_L5", 20_000, seed=3)
         d = Demod(symrate=cfg["symrate"], oqpsk=cfg["oqpsk"], bps=cfg["bps"], rrc_order=cfg["order"],
                   interp_factor=cfg["interp"], kernel="auto")
-        assert d.kernel_name() == "simple"
+        assert d.kernel_name() == served_by
         soft, counts, symf = d.process_batch(raw.reshape(1, -1), want_float=True)
         o = oracle_mod.Oracle(**cfg)
         w = o.process(raw)
