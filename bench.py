@@ -44,7 +44,7 @@ FS = 230000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
@@ -67,25 +67,52 @@ def parse():
 # ------------------------------------------------------------------ clocks sampler --
 
 class Clocks:
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML every 20 ms
+    (nvidia-smi every 100 ms if the NVML binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self.nvml, self.source = None, "nvidia-smi"
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.dev) / 1000.0
+        try:
+            rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+        except Exception:
+            rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+        bits = (0x8, 0x40, 0x20, 0x4)      # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        return [sm, self.max_sm, pw] + ["Active" if rs & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 7:
+                        self.rows.append(f)
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.02 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.t.start()
@@ -99,10 +126,9 @@ class Clocks:
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm = sorted(float(r[0]) for r in self.rows)
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(str(r[3 + i]).lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------ CPU reference ---

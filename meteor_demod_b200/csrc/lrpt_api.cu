@@ -37,8 +37,10 @@ struct lrpt_demod {
 	lrpt_state_t *d_snap   = nullptr;   /* [nstreams] lrpt_snapshot */
 	float2       *d_snap_hist = nullptr;
 	lrpt_state_t *h_state  = nullptr;   /* pinned scratch, one state */
-	cudaStream_t  stream = nullptr, copy_stream = nullptr;
-	cudaEvent_t   ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+	cudaStream_t  stream = nullptr, copy_stream = nullptr, out_stream = nullptr;
+	cudaEvent_t   ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_cnt[2] = {nullptr, nullptr};
+	uint32_t     *d_mm = nullptr;       /* [2][2] min/max append cursor after a slab */
+	uint32_t     *h_mm = nullptr;       /* pinned copy */
 	/* staging for the host-buffer entry points (grown on demand) */
 	void   *d_raw[2] = {nullptr, nullptr}; size_t d_raw_bytes = 0;
 	int8_t *d_soft = nullptr; size_t d_soft_bytes = 0;
@@ -131,10 +133,14 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 	CUC(cudaSetDevice(p->device));
 	CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	CUC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+	CUC(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) {
 		CUC(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&h->ev_cnt[i], cudaEventDisableTiming));
 	}
+	CUC(cudaMalloc(&h->d_mm, 4*sizeof(uint32_t)));
+	CUC(cudaMallocHost(&h->h_mm, 4*sizeof(uint32_t)));
 	CUC(cudaMalloc(&h->d_taps, sizeof(float)*h->taps.size()));
 	CUC(cudaMalloc(&h->d_states, sizeof(lrpt_state_t)*p->nstreams));
 	CUC(cudaMalloc(&h->d_init, sizeof(lrpt_state_t)*p->nstreams));
@@ -189,6 +195,9 @@ extern "C" void lrpt_destroy(lrpt_demod_t *h)
 	cudaSetDevice(h->p.device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+	if (h->out_stream) cudaStreamSynchronize(h->out_stream);
+	cudaFree(h->d_mm);
+	if (h->h_mm) cudaFreeHost(h->h_mm);
 	cudaFree(h->d_taps); cudaFree(h->d_states); cudaFree(h->d_init); cudaFree(h->d_snap); cudaFree(h->d_snap_hist); cudaFree(h->d_hist); cudaFree(h->d_nsym); cudaFree(h->d_off); cudaFree(h->d_fallbacks);
 	cudaFree(h->d_raw[0]); cudaFree(h->d_raw[1]); cudaFree(h->d_soft); cudaFree(h->d_symf);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -196,7 +205,9 @@ extern "C" void lrpt_destroy(lrpt_demod_t *h)
 	for (int i = 0; i < 2; i++) {
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+		if (h->ev_cnt[i]) cudaEventDestroy(h->ev_cnt[i]);
 	}
+	if (h->out_stream) cudaStreamDestroy(h->out_stream);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	delete h;
@@ -308,6 +319,24 @@ static int ensure(lrpt_demod *h, void **ptr, size_t *have, size_t need)
 	return LRPT_OK;
 }
 
+/* smallest and largest append cursor of a batch: bounds the columns a slab added to d_soft */
+__global__ void cursor_minmax_kernel(const uint32_t *off, int n, uint32_t *mm)
+{
+	__shared__ uint32_t smin[32], smax[32];
+	uint32_t lo = 0xffffffffu, hi = 0u;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t v = off[i]; lo = min(lo, v); hi = max(hi, v); }
+	for (int d = 16; d > 0; d >>= 1) {
+		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+		hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+	}
+	if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (unsigned w = 1; w < blockDim.x/32; w++) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+		mm[0] = lo; mm[1] = hi;
+	}
+}
+
 /*
  * Host-buffer batch over streams [first, first+count): time slabs are copied to the
  * device on copy_stream while the previous slab is demodulated on stream (two raw
@@ -342,7 +371,23 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 	if (sym_f32 && (rc = ensure(h, (void **)&h->d_symf, &h->d_symf_bytes, d_symf_pitch*count))) return rc;
 	CU(h, cudaMemsetAsync(h->d_off, 0, sizeof(uint32_t)*count, h->stream));
 
+	/* Symbols go back to the host slab by slab, on a third stream, while the next slabs are still being
+	 * copied in and demodulated (the link is full duplex): after slab j every stream's cursor lies in
+	 * [min_j, max_j], so the columns [min_{j-1}, max_j) of d_soft hold everything slab j appended.
+	 * Columns past a stream's own cursor are copied too and are rewritten by the next slab's copy. */
 	size_t done = 0; int j = 0;
+	uint32_t col_from = 0;
+	auto flush_slab = [&](int b) -> int {                           /* symbols of the slab that used buffer b */
+		CU(h, cudaEventSynchronize(h->ev_cnt[b]));
+		const uint32_t lo = h->h_mm[2*b], hi = h->h_mm[2*b + 1] < cap ? h->h_mm[2*b + 1] : (uint32_t)cap;
+		if (hi > col_from) {
+			CU(h, cudaStreamWaitEvent(h->out_stream, h->ev_cnt[b], 0));
+			CU(h, cudaMemcpy2DAsync(soft + 2*(size_t)col_from, soft_stride, h->d_soft + 2*(size_t)col_from, d_soft_pitch,
+			                        2*(size_t)(hi - col_from), count, cudaMemcpyDeviceToHost, h->out_stream));
+		}
+		if (lo > col_from) col_from = lo < cap ? lo : (uint32_t)cap;
+		return LRPT_OK;
+	};
 	while (done < nsamples) {
 		const size_t n = (nsamples - done < slab) ? nsamples - done : slab;
 		const int b = j & 1;
@@ -355,6 +400,8 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 			                        n*bpsm, count, cudaMemcpyHostToDevice, h->copy_stream));
 		CU(h, cudaEventRecord(h->ev_copy[b], h->copy_stream));
 		CU(h, cudaStreamWaitEvent(h->stream, h->ev_copy[b], 0));
+		if (j >= 1 && (rc = flush_slab(b ^ 1))) return rc;          /* previous slab out while this one comes in;
+		                                                               also frees ev_cnt[b]/h_mm[b] (slab j-2 was flushed at j-1) */
 		LaunchArgs a{};
 		a.d_raw = h->d_raw[b]; a.raw_stride = d_raw_pitch; a.nsamples = n;
 		a.d_soft = h->d_soft; a.soft_stride = d_soft_pitch; a.cap = (unsigned)cap;
@@ -363,8 +410,12 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 		a.first_stream = first; a.nstreams = count;
 		if ((rc = launch(h, a, h->stream))) return rc;
 		CU(h, cudaEventRecord(h->ev_done[b], h->stream));
+		cursor_minmax_kernel<<<1, 1024, 0, h->stream>>>(h->d_off, count, h->d_mm + 2*b);
+		CU(h, cudaMemcpyAsync(h->h_mm + 2*b, h->d_mm + 2*b, 2*sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+		CU(h, cudaEventRecord(h->ev_cnt[b], h->stream));
 		done += n; j++;
 	}
+	if (j >= 1 && (rc = flush_slab((j - 1) & 1))) return rc;
 	CU(h, cudaMemcpyAsync(h->h_counts, h->d_off, sizeof(uint32_t)*count, cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
 	uint32_t most = 0; int over = 0;
@@ -374,14 +425,11 @@ static int process_host(lrpt_demod *h, int first, int count, const void *raw_iq,
 		if (stored > cap) { stored = (uint32_t)cap; over = 1; }
 		if (stored > most) most = stored;
 	}
-	if (most) {
-		CU(h, cudaMemcpy2DAsync(soft, soft_stride, h->d_soft, d_soft_pitch, 2*(size_t)most, count,
+	if (most && sym_f32)
+		CU(h, cudaMemcpy2DAsync(sym_f32, symf_stride, h->d_symf, d_symf_pitch, 8*(size_t)most, count,
 		                        cudaMemcpyDeviceToHost, h->stream));
-		if (sym_f32)
-			CU(h, cudaMemcpy2DAsync(sym_f32, symf_stride, h->d_symf, d_symf_pitch, 8*(size_t)most, count,
-			                        cudaMemcpyDeviceToHost, h->stream));
-		CU(h, cudaStreamSynchronize(h->stream));
-	}
+	CU(h, cudaStreamSynchronize(h->stream));
+	CU(h, cudaStreamSynchronize(h->out_stream));
 	return over ? fail(h, LRPT_ERR_CAP, "a stream produced more than cap=%zu symbols", cap) : LRPT_OK;
 }
 
