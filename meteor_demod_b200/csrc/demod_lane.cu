@@ -38,7 +38,6 @@ constexpr int LN_T         = 16;   /* samples per tile (per lane)               
 constexpr int LN_MAX_WARPS = 16;   /* warps per CTA = 512 streams                          */
 constexpr int LN_MAX_TAPS  = 1025;
 constexpr int LN_MAX_L     = 8;
-constexpr int LN_LP        = 8;    /* floats per row of the transposed tap table [taps][LN_LP] */
 
 #ifndef LRPT_LANE_CVT
 #define LRPT_LANE_CVT 1            /* 0: integer->float conversion instructions, 1: exponent-splice + subtract */
@@ -75,6 +74,7 @@ struct LaneArgs {
 	int           W;           /* warps per CTA */
 	int           NT;          /* tiles per window epoch */
 	int           nco_n0;
+	int           TS;          /* floats per bank of the tap table: >= taps, a multiple of 4, TS/4 odd */
 	int           div_magic;   /* (x*div_magic) >> 16 == x / interp for 0 <= x < LN_T*interp */
 	float         one;         /* 1.0f, opaque to the compiler (see the packed f32x2 helpers) */
 };
@@ -207,54 +207,49 @@ LRPT_DEV void tile_store(typename RawT<BPS>::elem *col, int e0, const uint4 (&pf
 }
 
 /* filter_get(flt, i), filter.c:46-65: w = this lane's column at the entry of the oldest sample,
- * hb = taps table at this lane's bank (row stride LP). acc = acc + x*h, oldest first, multiply
- * and add rounded separately. */
-template <int BPS, int LP>
+ * hb = this lane's bank of the tap table (16-byte aligned, taps contiguous). acc = acc + x*h,
+ * oldest first, multiply and add rounded separately; (re, im) ride one packed f32x2 chain.
+ * Coefficients arrive four at a time (lanes on different banks hit different bank groups). */
+#if LRPT_LANE_PACKED
+#define LN_TAP(X, H) acc = fma2(mul2(R::cvt2(X), pk2((H), (H))), one2, acc)
+#else
+#define LN_TAP(X, H) do { const float2 x_ = R::cvt(X); ar = __fadd_rn(ar, __fmul_rn(x_.x, (H))); ai = __fadd_rn(ai, __fmul_rn(x_.y, (H))); } while (0)
+#endif
+template <int BPS>
 LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb, int taps, float one)
 {
 	typedef RawT<BPS> R;
 #if LRPT_LANE_PACKED
 	f32x2_t acc = pk2(0.0f, 0.0f);
 	const f32x2_t one2 = pk2(one, one);
-	int k = 0;
-#pragma unroll 1
-	for (; k + 8 <= taps; k += 8) {
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const float h = hb[(k + j)*LP];
-			acc = fma2(mul2(R::cvt2(w[(k + j)*32]), pk2(h, h)), one2, acc);
-		}
-	}
-#pragma unroll 1
-	for (; k < taps; k++) {
-		const float h = hb[k*LP];
-		acc = fma2(mul2(R::cvt2(w[k*32]), pk2(h, h)), one2, acc);
-	}
-	return upk2(acc);
 #else
 	(void)one;
 	float ar = 0.0f, ai = 0.0f;
-	int k = 0;
+#endif
+	int left = taps;
 #pragma unroll 1
-	for (; k + 8 <= taps; k += 8) {
+	for (; left >= 16; left -= 16, w += 16*32, hb += 16) {
 #pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const float2 x = R::cvt(w[(k + j)*32]);
-			const float h = hb[(k + j)*LP];
-			ar = __fadd_rn(ar, __fmul_rn(x.x, h));
-			ai = __fadd_rn(ai, __fmul_rn(x.y, h));
+		for (int q = 0; q < 4; q++) {
+			const float4 h4 = *reinterpret_cast<const float4 *>(hb + 4*q);
+			LN_TAP(w[(4*q + 0)*32], h4.x); LN_TAP(w[(4*q + 1)*32], h4.y);
+			LN_TAP(w[(4*q + 2)*32], h4.z); LN_TAP(w[(4*q + 3)*32], h4.w);
 		}
 	}
 #pragma unroll 1
-	for (; k < taps; k++) {
-		const float2 x = R::cvt(w[k*32]);
-		const float h = hb[k*LP];
-		ar = __fadd_rn(ar, __fmul_rn(x.x, h));
-		ai = __fadd_rn(ai, __fmul_rn(x.y, h));
+	for (; left >= 4; left -= 4, w += 4*32, hb += 4) {
+		const float4 h4 = *reinterpret_cast<const float4 *>(hb);
+		LN_TAP(w[0*32], h4.x); LN_TAP(w[1*32], h4.y); LN_TAP(w[2*32], h4.z); LN_TAP(w[3*32], h4.w);
 	}
+#pragma unroll 1
+	for (; left > 0; left--, w += 32, hb++) LN_TAP(w[0], hb[0]);
+#if LRPT_LANE_PACKED
+	return upk2(acc);
+#else
 	return make_float2(ar, ai);
 #endif
 }
+#undef LN_TAP
 
 /* ------------------------------------------------------------- kernel ------ */
 
@@ -264,7 +259,6 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 {
 	typedef RawT<BPS> R;
 	typedef typename R::elem elem;
-	constexpr int LP = LN_LP;
 	constexpr int T = LN_T;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -274,13 +268,13 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	float *lut = reinterpret_cast<float *>(smem_raw);               /* [32] */
-	float *hT  = lut + 32;                                          /* [taps][LP] */
-	elem *wins = reinterpret_cast<elem *>(hT + ((taps*LP + 3) & ~3));   /* [W][NE][32] */
+	float *hT  = lut + 32;                                          /* [L][TS]: bank p, tap k at hT[p*TS + k] */
+	elem *wins = reinterpret_cast<elem *>(hT + L*a.TS);            /* [W][NE][32] */
 
 	if (threadIdx.x < 32) lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
-	for (int i = threadIdx.x; i < taps*LP; i += blockDim.x) {
-		const int k = i/LP, p = i - k*LP;
-		hT[i] = (p < L) ? a.taps[p*taps + k] : 0.0f;
+	for (int i = threadIdx.x; i < L*a.TS; i += blockDim.x) {
+		const int p = i/a.TS, k = i - p*a.TS;
+		hT[i] = (k < taps) ? a.taps[p*taps + k] : 0.0f;
 	}
 	__syncthreads();
 
@@ -295,6 +289,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	Loop r;
 	long long nsymbols = 0, first_lock = -1;
 	unsigned off = 0, nsym = 0;
+	int lock_at = -1;                                               /* symbol of this launch at which the PLL had locked once */
 	char2 *out = nullptr; float2 *outf = nullptr; uint32_t *outq = nullptr;
 	loop_load(r, a.states[a.first_stream + lrow]);
 	if (active) {
@@ -336,7 +331,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 		 * a crossing inside the tile takes its FIR + symbol step, all together. */
 		while (true) {
 			if (active && !have_x && Q < q1)
-				have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
+				have_x = nco_to_crossing4(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
 			__syncwarp();
 			const bool ready = active && have_x && Qx < q1;
 			if (!__any_sync(0xffffffffu, ready)) break;
@@ -344,7 +339,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				/* filter_get(flt, i) at sub-step Qx = n*L + i (demod.c:33-35) */
 				const int dq = Qx - q0;
 				const int nr = (dq*a.div_magic) >> 16, i = dq - nr*L;       /* sample within the tile, sub-step */
-				const float2 y = fir_lazy<BPS, LP>(col + (te*T + nr)*32, hT + (L - 1 - i), taps, a.one);
+				const float2 y = fir_lazy<BPS>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one);
 				const Loop saved = r;
 				float ore, oim; bool emitted; Osc next;
 				if (!symbol_fast_osc<OQ>(r, c, lut, half, y.x, y.y, osc, ore, oim, emitted, next)) {
@@ -354,13 +349,13 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				}
 				osc = next;
 				if (emitted) {
-					if (r.locked_once && first_lock < 0) first_lock = nsymbols;
+					lock_at = (r.locked_once && lock_at < 0) ? (int)nsym : lock_at;
 					if (off + nsym < a.cap) {
 						out[off + nsym] = make_char2((signed char)quantise(ore), (signed char)quantise(oim));
 						if (AUX && outf) outf[off + nsym] = make_float2(ore, oim);
 						if (AUX && outq) outq[off + nsym] = a.q_base + (uint32_t)Qx;
 					}
-					nsym++; nsymbols++;
+					nsym++;
 				}
 				have_x = false;
 			}
@@ -384,8 +379,8 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 		}
 		loop_store(r, a.states[sid]);
 		a.states[sid].nsamples += a.nsamples;
-		a.states[sid].nsymbols = nsymbols;
-		a.states[sid].first_lock_symbol = first_lock;
+		a.states[sid].nsymbols = nsymbols + nsym;
+		a.states[sid].first_lock_symbol = (first_lock < 0 && lock_at >= 0) ? nsymbols + lock_at : first_lock;   /* main.c:312 */
 		if (a.nsym_out) a.nsym_out[local] = nsym;
 		if (a.out_off) a.out_off[local] = off + nsym;
 	}
@@ -395,10 +390,14 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 
 static int ln_num_sms = 0, ln_max_smem = 0;
 
-static size_t ln_fixed_smem(int taps)
+static int ln_ts(int taps)
 {
-	return 32*sizeof(float) + (size_t)((taps*LN_LP + 3) & ~3)*sizeof(float);
+	int ts = 4*((taps + 3)/4);
+	if (((ts/4) & 1) == 0) ts += 4;                /* TS/4 odd: banks of the table start in different bank groups */
+	return ts;
 }
+
+static size_t ln_fixed_smem(int taps, int L) { return 32*sizeof(float) + (size_t)L*ln_ts(taps)*sizeof(float); }
 
 static size_t ln_warp_smem(int taps, int NT, int bps) { return (size_t)((taps - 1) + NT*LN_T)*32*(size_t)(bps/4); }
 
@@ -441,7 +440,7 @@ cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 {
 	const lrpt_consts_t &c = *a.c;
 	const int L = c.interp, taps = c.taps;
-	const size_t fixed = ln_fixed_smem(taps);
+	const size_t fixed = ln_fixed_smem(taps, L);
 	/* warps per CTA: spread the batch over every SM first, then stack warps (one CTA per SM). The
 	 * window epoch is at least 2 tiles (the head move is an in-place ascending copy, so it may
 	 * overlap its source) and as long as shared memory allows, which amortises that move. */
@@ -476,8 +475,9 @@ cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 		{
 			const double nominal = (c.oqpsk ? 3.14159265358979 : 6.28318530717959)/(double)c.t_center;
 			const int cmin = (int)nominal - 1;
-			w.nco_n0 = cmin > 1 ? 4*((cmin - 1)/4) : 0;
+			w.nco_n0 = cmin > 1 ? cmin - 1 : 0;                      /* tested sums: cmin .. cmin+3 */
 		}
+		w.TS = ln_ts(taps);
 		w.one = 1.0f;
 		w.div_magic = (65536 + L - 1)/L;
 		for (int x = 0; x < LN_T*L; x++)

@@ -159,5 +159,37 @@ LRPT_DEV bool nco_to_crossing(Loop &r, const lrpt_consts_t &c, int n0, int &Q, i
 	return found;
 }
 
+/*
+ * The same search with a 4-sum tested window behind n0 plain adds, n0 any warp-uniform count
+ * (demod_lane.cu: n0 = nominal - 2, so the window is the four counts a locked loop produces).
+ */
+LRPT_DEV bool nco_to_crossing4(Loop &r, const lrpt_consts_t &c, int n0, int &Q, int q1, int Qend,
+                               int &Qx, int &half)
+{
+	const float f = r.t_freq;
+	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
+	float p = r.t_phase;
+	switch (n0 & 3) {                                               /* warp-uniform */
+		case 3: p = __fadd_rn(p, f);
+		case 2: p = __fadd_rn(p, f);
+		case 1: p = __fadd_rn(p, f);
+		default: break;
+	}
+	for (int b = n0 >> 2; b > 0; b--) {
+		p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f);
+	}
+	const float s0 = __fadd_rn(p, f), s1 = __fadd_rn(s0, f), s2 = __fadd_rn(s1, f), s3 = __fadd_rn(s2, f);
+	const bool c0 = s0 >= thr, c1 = s1 >= thr, c2 = s2 >= thr, c3 = s3 >= thr;
+	if (f > 0.0f && !(p >= thr) && (c0 || c1 || c2 || c3) && Q + n0 + 4 <= Qend) {
+		const int first = c0 ? 0 : c1 ? 1 : c2 ? 2 : 3;             /* sums are non-decreasing: first crossing */
+		r.t_phase = c0 ? s0 : c1 ? s1 : c2 ? s2 : s3;
+		Qx = Q + n0 + first; Q = Qx + 1;
+		if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
+		return true;
+	}
+	bool found = false;
+	while (!found && Q < q1) found = nco_chunk(r, c, Q, Qend, Qx, half);
+	return found;
+}
 
 } // namespace lrpt
