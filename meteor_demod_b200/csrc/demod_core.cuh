@@ -438,4 +438,96 @@ LRPT_DEV bool symbol_fast_osc(Loop &r, const lrpt_consts_t &c, const float *lut,
 	return !bad;
 }
 
+/* ------------------------------------------------- fast path, split in two ----
+ *
+ * Within one stream, what the NEXT timing decision waits for is short: delay-line output ->
+ * bias/gain scaling -> NCO mix -> retime (demod.c:35-39). Everything else a symbol step does --
+ * the AGC magnitude and gain update (agc.c:20-22), the Costas NCO advance, phase-error, loop
+ * and lock-detector update (pll.c:61-62,100-130), the oscillator values of the new phase -- is
+ * not needed before the next filter output has been MIXED. demod_lane.cu therefore runs
+ * step_critical at once and weaves step_deferred_fast of symbol k into the tap loop of symbol
+ * k+1, where its long double-precision chains cost no time. Values and order of evaluation per
+ * variable are unchanged; step_deferred_exact is the statement-by-statement version the caller
+ * falls back to when a shortcut of the fast one is not provably exact (same rules as symbol_fast).
+ */
+struct Pend { float sr, si, ore, oim; int half; };
+
+template <bool OQ>
+LRPT_DEV void step_critical(Loop &r, const lrpt_consts_t &c, int half, float re, float im,
+                            float s, float co, Pend &p)
+{
+	const float keep = 1.0f - 0.001f;                               /* agc_apply up to the scaled sample */
+	r.bias_re = __fadd_rn(__fmul_rn(r.bias_re, keep), __fmul_rn(0.001f, re));
+	r.bias_im = __fadd_rn(__fmul_rn(r.bias_im, keep), __fmul_rn(0.001f, im));
+	const float sr = __fmul_rn(__fsub_rn(re, r.bias_re), r.gain);
+	const float si = __fmul_rn(__fsub_rn(im, r.bias_im), r.gain);
+	p.sr = sr; p.si = si; p.half = half;
+	if (OQ && half == 1) {                                          /* demod.c:66-71 */
+		r.oq_inphase = __fsub_rn(__fmul_rn(sr, co), __fmul_rn(si, s));
+		return;
+	}
+	if (OQ) {                                                       /* demod.c:72-83 */
+		p.oim = __fadd_rn(__fmul_rn(sr, s), __fmul_rn(si, co));
+		p.ore = r.oq_inphase;
+	} else {                                                        /* pll_mix, pll.c:60 */
+		p.ore = __fsub_rn(__fmul_rn(sr, co), __fmul_rn(si, s));
+		p.oim = __fadd_rn(__fmul_rn(sr, s), __fmul_rn(si, co));
+	}
+	retime(r, c, p.oim);                                            /* timing.c:60-95 */
+}
+
+/* branch-free; returns false when a shortcut was not provably exact (then nothing it wrote may be used) */
+template <bool OQ>
+LRPT_DEV bool step_deferred_fast(Loop &r, const lrpt_consts_t &c, const float *lut, const Pend &p, Osc &next)
+{
+	bool bad = false;
+	const double da = (double)p.sr, db = (double)p.si;              /* agc.c:20-22 */
+	const float mag = sqrt_to_float_fast(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)), bad);
+	const float g = __fadd_rn(r.gain, __fmul_rn(0.0001f, __fsub_rn(190.0f, mag)));
+	r.gain = (0.0f > g) ? 0.0f : g;
+
+	const float p1 = __fadd_rn(r.p_phase, r.p_freq);                /* pll.c:61-62 */
+	const float pw = __double2float_rn(__dsub_rn((double)p1, kTwoPiD));
+	const float p2 = (p1 >= kTwoPiF) ? pw : p1;
+	const bool arm_i = OQ && p.half == 1;                           /* I arm: NCO advance only */
+
+	const float error = __fsub_rn(__fmul_rn(lut_tanh(lut, p.ore), p.oim), __fmul_rn(lut_tanh(lut, p.oim), p.ore));
+	const float ph = arm_i ? p2 : __fadd_rn(p2, __fmul_rn(c.p_alpha, error));
+	bad |= !(fabsf(ph) < kTwoPiF);                                  /* else fmod really reduces (pll.c:113) */
+	r.p_phase = ph;
+	next = osc_for(ph);
+	bad |= next.bad;
+
+	const float f1 = __fadd_rn(r.p_freq, __fmul_rn(c.p_beta, error));
+	const float e1 = __double2float_rn(__dadd_rn((double)__fmul_rn(r.p_err, 1.0f - 0.001f),
+	                                             __dmul_rn(fabs((double)error), (double)0.001f)));
+	const int was = r.locked;
+	const int acquire = (e1 < 85.0f && !was) ? 1 : 0;
+	const int now = acquire ? 1 : ((e1 > 105.0f && was) ? 0 : was);
+	const float fsw = __double2float_rn(__dadd_rn((double)f1, r.updown > 0 ? 0.000001 : -0.000001));
+	const float f2 = now ? f1 : fsw;
+	const int up1 = (f2 <= -c.p_fmax) ? 1 : r.updown;
+	const int up2 = (f2 >= c.p_fmax) ? -1 : up1;
+	const float f3 = (c.p_fmax < f2) ? c.p_fmax : f2;
+	const float f4 = (-c.p_fmax > f3) ? -c.p_fmax : f3;
+	r.p_err = arm_i ? r.p_err : e1;
+	r.locked = arm_i ? was : now;
+	r.locked_once |= arm_i ? 0 : acquire;
+	r.updown = arm_i ? r.updown : up2;
+	r.p_freq = arm_i ? r.p_freq : f4;
+	return !bad;
+}
+
+template <bool OQ>
+LRPT_DEV void step_deferred_exact(Loop &r, const lrpt_consts_t &c, const float *lut, const Pend &p, Osc &next)
+{
+	const float g = __fadd_rn(r.gain, __fmul_rn(0.0001f, __fsub_rn(190.0f, cabsf_exact(p.sr, p.si))));
+	r.gain = (0.0f > g) ? 0.0f : g;
+	pll_advance(r);
+	if (!(OQ && p.half == 1)) pll_update(r, c, lut, p.ore, p.oim);
+	next.s = fast_sin(-r.p_phase);
+	next.co = fast_cos(-r.p_phase);
+	next.bad = false;
+}
+
 } // namespace lrpt

@@ -42,6 +42,9 @@ constexpr int LN_MAX_L     = 8;
 #ifndef LRPT_LANE_CVT
 #define LRPT_LANE_CVT 1            /* 0: integer->float conversion instructions, 1: exponent-splice + subtract */
 #endif
+#ifndef LRPT_LANE_PIPE
+#define LRPT_LANE_PIPE 1           /* 1: deferred half of symbol k woven into the tap loop of symbol k+1 */
+#endif
 #ifndef LRPT_LANE_PACKED
 #define LRPT_LANE_PACKED 1         /* 1: the I and Q chains as one packed f32x2 chain (sm_100 FMUL2/FFMA2/FADD2) */
 #endif
@@ -249,6 +252,58 @@ LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const f
 	return make_float2(ar, ai);
 #endif
 }
+
+/* The same filter with the DEFERRED half of the previous symbol step (demod_core.cuh, "split in two")
+ * placed in the basic block of the first 64 taps: ptxas interleaves its long double-precision
+ * chains with the issue-bound tap arithmetic, so they no longer cost time of their own. */
+template <int BPS, bool OQ>
+LRPT_DEV float2 fir_lazy_with_deferred(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb,
+                                       int taps, float one, Loop &r, const lrpt_consts_t &c, const float *lut,
+                                       const Pend &pd, Osc &next, bool &ok)
+{
+	typedef RawT<BPS> R;
+#if LRPT_LANE_PACKED
+	f32x2_t acc = pk2(0.0f, 0.0f);
+	const f32x2_t one2 = pk2(one, one);
+#else
+	(void)one;
+	float ar = 0.0f, ai = 0.0f;
+#endif
+	int left = taps;
+	if (left >= 64) {
+		ok = step_deferred_fast<OQ>(r, c, lut, pd, next);
+#pragma unroll
+		for (int q = 0; q < 16; q++) {
+			const float4 h4 = *reinterpret_cast<const float4 *>(hb + 4*q);
+			LN_TAP(w[(4*q + 0)*32], h4.x); LN_TAP(w[(4*q + 1)*32], h4.y);
+			LN_TAP(w[(4*q + 2)*32], h4.z); LN_TAP(w[(4*q + 3)*32], h4.w);
+		}
+		left -= 64; w += 64*32; hb += 64;
+	} else {
+		ok = step_deferred_fast<OQ>(r, c, lut, pd, next);
+	}
+#pragma unroll 1
+	for (; left >= 16; left -= 16, w += 16*32, hb += 16) {
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const float4 h4 = *reinterpret_cast<const float4 *>(hb + 4*q);
+			LN_TAP(w[(4*q + 0)*32], h4.x); LN_TAP(w[(4*q + 1)*32], h4.y);
+			LN_TAP(w[(4*q + 2)*32], h4.z); LN_TAP(w[(4*q + 3)*32], h4.w);
+		}
+	}
+#pragma unroll 1
+	for (; left >= 4; left -= 4, w += 4*32, hb += 4) {
+		const float4 h4 = *reinterpret_cast<const float4 *>(hb);
+		LN_TAP(w[0*32], h4.x); LN_TAP(w[1*32], h4.y); LN_TAP(w[2*32], h4.z); LN_TAP(w[3*32], h4.w);
+	}
+#pragma unroll 1
+	for (; left > 0; left--, w += 32, hb++) LN_TAP(w[0], hb[0]);
+#if LRPT_LANE_PACKED
+	return upk2(acc);
+#else
+	return make_float2(ar, ai);
+#endif
+}
 #undef LN_TAP
 
 /* ------------------------------------------------------------- kernel ------ */
@@ -313,7 +368,14 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	const int Qend = a.nsamples*L;
 	int Q = 0;
 	bool have_x = false; int Qx = 0, half = 0;
+#if LRPT_LANE_PIPE
+	Osc osc; osc.s = fast_sin(-r.p_phase); osc.co = fast_cos(-r.p_phase); osc.bad = false;   /* pll.c:53-54 */
+	Pend pd; pd.sr = pd.si = pd.ore = pd.oim = 1.0f; pd.half = 0;
+	bool pend = false;                                              /* a deferred half is outstanding */
+	int pd_q = 0;
+#else
 	Osc osc = osc_for(r.p_phase);                                   /* fast_sin/fast_cos(-p_phase), pll.c:53-54 */
+#endif
 	int ep0 = 0;                                                    /* first sample of the window epoch */
 
 	for (int t = 0; t < ntiles; t++) {
@@ -339,6 +401,34 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				/* filter_get(flt, i) at sub-step Qx = n*L + i (demod.c:33-35) */
 				const int dq = Qx - q0;
 				const int nr = (dq*a.div_magic) >> 16, i = dq - nr*L;       /* sample within the tile, sub-step */
+#if LRPT_LANE_PIPE
+				/* deferred half of the previous symbol, woven into this symbol's taps */
+				const float s_gain = r.gain, s_pp = r.p_phase, s_pf = r.p_freq, s_pe = r.p_err;
+				const int s_lk = r.locked, s_lo = r.locked_once, s_ud = r.updown;
+				Osc next; bool ok;
+				const float2 y = fir_lazy_with_deferred<BPS, OQ>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one,
+				                                                 r, c, lut, pd, next, ok);
+				if (!(ok && pend)) {                                 /* rare: nothing was outstanding (first event of the
+				                                                        launch), or a shortcut was not provably exact */
+					r.gain = s_gain; r.p_phase = s_pp; r.p_freq = s_pf; r.p_err = s_pe;
+					r.locked = s_lk; r.locked_once = s_lo; r.updown = s_ud;
+					if (pend) step_deferred_exact<OQ>(r, c, lut, pd, next);
+					else next = osc;
+				}
+				if (pend && !(OQ && pd.half == 1)) {
+					lock_at = (r.locked_once && lock_at < 0) ? (int)nsym : lock_at;
+					if (off + nsym < a.cap) {
+						out[off + nsym] = make_char2((signed char)quantise(pd.ore), (signed char)quantise(pd.oim));
+						if (AUX && outf) outf[off + nsym] = make_float2(pd.ore, pd.oim);
+						if (AUX && outq) outq[off + nsym] = a.q_base + (uint32_t)pd_q;
+					}
+					nsym++;
+				}
+				osc = next;
+				/* the half of THIS symbol the next timing decision waits for */
+				step_critical<OQ>(r, c, half, y.x, y.y, osc.s, osc.co, pd);
+				pend = true; pd_q = Qx;
+#else
 				const float2 y = fir_lazy<BPS>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one);
 				const Loop saved = r;
 				float ore, oim; bool emitted; Osc next;
@@ -357,6 +447,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 					}
 					nsym++;
 				}
+#endif
 				have_x = false;
 			}
 			__syncwarp();
@@ -369,6 +460,22 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 			ep0 += NT*T;
 		}
 	}
+
+#if LRPT_LANE_PIPE
+	if (active && pend) {                                           /* the last symbol's deferred half */
+		Osc next;
+		step_deferred_exact<OQ>(r, c, lut, pd, next);
+		if (!(OQ && pd.half == 1)) {
+			lock_at = (r.locked_once && lock_at < 0) ? (int)nsym : lock_at;
+			if (off + nsym < a.cap) {
+				out[off + nsym] = make_char2((signed char)quantise(pd.ore), (signed char)quantise(pd.oim));
+				if (AUX && outf) outf[off + nsym] = make_float2(pd.ore, pd.oim);
+				if (AUX && outq) outq[off + nsym] = a.q_base + (uint32_t)pd_q;
+			}
+			nsym++;
+		}
+	}
+#endif
 
 	/* epilogue: the last taps-1 samples are the next call's delay line */
 	if (active) {

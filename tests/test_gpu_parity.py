@@ -221,3 +221,66 @@ def test_long_push_is_split_transparently(lib):
     assert n1 == na + nb
     assert torch.equal(s1[0, : 2 * na], sa[0, : 2 * na]) and torch.equal(s1[0, 2 * na: 2 * n1], sb[0, : 2 * nb])
     assert d1.export_state() == d2.export_state()
+
+
+@pytest.mark.parametrize("name", ["C1_qpsk72k_s16_o32_L5", "C2_oqpsk80k_u8_o32_L5"])
+def test_lane_kernel_many_warps_per_sm(name, oracle_mod, lib):
+    """10 000 streams = 313 warps over 148 SMs (3 warps per CTA, idle lanes in the last warp): streams
+    sampled across warps, CTAs and the tail are compared with the oracle, all others with their twins
+    (stream s and s + 5000 carry the same input)."""
+    import torch
+    cfg = CONFIGS[name]
+    half, n = 5000, 6000
+    base = [make_case(name, n + 1024, seed=200 + k, cfo_hz=-300.0 + 40 * k) for k in range(16)]
+    rows = np.stack([base[s % 16][2 * ((s * 37) % 997): 2 * ((s * 37) % 997) + 2 * n] for s in range(half)])
+    raw = np.concatenate([rows, rows])
+    d = demod_for(cfg, "lane", nstreams=2 * half)
+    cap16 = (d.capacity(n) + 7) // 8 * 8
+    t_raw = torch.from_numpy(raw).cuda()
+    t_soft = torch.zeros((2 * half, 2 * cap16), dtype=torch.int8, device="cuda")
+    d.process_device(t_raw, t_soft)
+    d.sync()
+    counts = d.counts().astype(np.int64)
+    soft = t_soft.cpu().numpy().reshape(2 * half, cap16, 2)
+    assert np.array_equal(counts[:half], counts[half:])
+    for s in range(half):
+        assert np.array_equal(soft[s, :counts[s]], soft[s + half, :counts[s]]), s
+    for s in [0, 1, 31, 32, 33, 95, 96, 4735, 4736, 4999, 5000, 7777, 9967, 9968, 9999]:
+        o = oracle_mod.Oracle(**cfg)
+        w = o.process(raw[s])
+        assert counts[s] == w.nsym, s
+        assert np.array_equal(soft[s, :w.nsym], w.soft), s
+        assert_state_equal(d.state(s), o)
+
+
+def test_full_size_batch_twins_and_samples(oracle_mod, lib):
+    """BASELINE-size batch (75776 streams = 16 warps on every SM): a size-independent property --
+    streams with identical input give identical output, checked over the WHOLE batch -- plus sampled
+    streams against the oracle."""
+    import torch
+    name = "C1_qpsk72k_s16_o32_L5"
+    cfg = CONFIGS[name]
+    half, n = 37888, 4096
+    base = [make_case(name, n + 2048, seed=300 + k, cfo_hz=-500.0 + 60 * k) for k in range(16)]
+    b = torch.from_numpy(np.stack(base)).cuda()                                   # [16, 2*(n+2048)]
+    s = torch.arange(half, device="cuda")
+    off = 2 * ((s * 53) % 1999)
+    idx = off[:, None] + torch.arange(2 * n, device="cuda")[None, :]
+    rows = b[(s % 16)[:, None], idx]
+    t_raw = torch.cat([rows, rows]).contiguous()
+    d = demod_for(cfg, "auto", nstreams=2 * half)
+    assert d.kernel_name() == "lane"
+    cap16 = (d.capacity(n) + 7) // 8 * 8
+    t_soft = torch.zeros((2 * half, 2 * cap16), dtype=torch.int8, device="cuda")
+    d.process_device(t_raw, t_soft)
+    d.sync()
+    counts = torch.from_numpy(d.counts().astype(np.int64)).cuda()
+    assert torch.equal(counts[:half], counts[half:])
+    valid = torch.arange(cap16, device="cuda")[None, :] < counts[:half, None]
+    a3, b3 = t_soft[:half].view(half, cap16, 2), t_soft[half:].view(half, cap16, 2)
+    assert bool(((a3 == b3).all(dim=2) | ~valid).all())
+    assert int(counts.min()) > 0.3 * n and int(counts.max()) < 0.33 * n
+    for i in [0, 511, 512, 20000, 37887, 37888, 75775]:
+        w = oracle_mod.Oracle(**cfg).process(t_raw[i].cpu().numpy())
+        got = t_soft[i, : 2 * w.nsym].cpu().numpy().reshape(-1, 2)
+        assert int(counts[i]) == w.nsym and np.array_equal(got, w.soft), i
