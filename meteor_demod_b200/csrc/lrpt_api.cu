@@ -508,6 +508,15 @@ extern "C" int lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, s
 	const lrpt_state_t *s = (const lrpt_state_t *)buf;
 	if (len != lrpt_state_size(h) || s->magic != LRPT_STATE_MAGIC || s->taps != (uint32_t)h->c.taps)
 		return fail(h, LRPT_ERR_STATE, "state blob: size/magic/taps mismatch");
+	if (h->p.bps != 32) {
+		/* the delay line of an 8/16-bit handle holds converted input samples (wavfile.c:58-66): integers of
+		 * that range. The lane kernel keeps them in the input's own type, so anything else is refused. */
+		const float *hv = (const float *)((const char *)buf + sizeof(lrpt_state_t));
+		const float lo = h->p.bps == 8 ? -128.0f : -32768.0f, hi = h->p.bps == 8 ? 127.0f : 32767.0f;
+		for (int i = 0; i < 2*h->H; i++)
+			if (!(hv[i] >= lo && hv[i] <= hi) || hv[i] != (float)(int)hv[i])
+				return fail(h, LRPT_ERR_STATE, "state blob: delay line holds a value no %d-bit input produces", h->p.bps);
+	}
 	CU(h, cudaSetDevice(h->p.device));
 	CU(h, cudaStreamSynchronize(h->stream));
 	CU(h, cudaMemcpy(h->d_states + stream, s, sizeof(*s), cudaMemcpyHostToDevice));

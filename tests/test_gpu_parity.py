@@ -105,6 +105,10 @@ def test_ragged_pushes_and_state_roundtrip(kernel, oracle_mod, lib):
     assert first == (int(np.argmax(want.lock_once)) if want.lock_once.any() else -1)
     with pytest.raises(Exception):
         d2.import_state(blob[:-8])
+    bad = bytearray(blob)
+    bad[-4:] = np.float32(0.5).tobytes()                   # no 16-bit input leaves 0.5 in the delay line
+    with pytest.raises(Exception):
+        d2.import_state(bytes(bad))
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -284,3 +288,35 @@ def test_full_size_batch_twins_and_samples(oracle_mod, lib):
         w = oracle_mod.Oracle(**cfg).process(t_raw[i].cpu().numpy())
         got = t_soft[i, : 2 * w.nsym].cpu().numpy().reshape(-1, 2)
         assert int(counts[i]) == w.nsym and np.array_equal(got, w.soft), i
+
+
+@pytest.mark.parametrize("kernel", ["lane", "simple"])
+def test_random_configurations(kernel, oracle_mod, lib):
+    """Seeded fuzz over the parameter space (order 0..140, oversampling 1..8, all three input types, both
+    modes, odd symbol rates, ragged two-part pushes, stream counts that leave idle lanes): soft symbols
+    and the complete state against the oracle."""
+    from meteor_demod_b200 import Demod, synth
+    rng = np.random.default_rng(20261017)
+    for case in range(28):
+        order = int(rng.choice([0, 1, 2, 3, 7, 8, 15, 16, 31, 33, 40, 63, 64, 100, 140]))
+        interp = int(rng.integers(1, 9))
+        bps = int(rng.choice([8, 16, 32]))
+        oq = int(rng.integers(0, 2))
+        symrate = int(rng.choice([72000, 80000, 57500, 91000, 33000]))
+        ns = int(rng.choice([1, 3, 33, 65]))
+        n = int(rng.integers(40, 7000))
+        cut = int(rng.integers(0, n + 1))
+        cfg = dict(symrate=symrate, oqpsk=oq, bps=bps, order=order, interp=interp)
+        raw = np.stack([synth.make_raw(n, symrate=symrate, oqpsk=bool(oq), bps=bps, seed=1000 + 7 * case + s,
+                                       cfo_hz=float(rng.integers(-900, 900))) for s in range(ns)])
+        d = Demod(symrate=symrate, oqpsk=oq, bps=bps, rrc_order=order, interp_factor=interp, nstreams=ns, kernel=kernel)
+        s1, c1 = d.process_batch(np.ascontiguousarray(raw[:, : 2 * cut]))
+        s2, c2 = d.process_batch(np.ascontiguousarray(raw[:, 2 * cut:]))
+        for s in range(ns):
+            o = oracle_mod.Oracle(**cfg)
+            w = o.process(raw[s])
+            got = np.concatenate([s1[s, : c1[s]], s2[s, : c2[s]]])
+            assert got.shape[0] == w.nsym, (case, cfg, ns, n, cut, s)
+            assert np.array_equal(got, w.soft), (case, cfg, ns, n, cut, s)
+            assert_state_equal(d.state(s), o)
+        d.close()

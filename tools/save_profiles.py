@@ -1,0 +1,52 @@
+"""Turn the files a profiling gpurun call brought back (gpurun_out/) into the committed summaries under profiles/:
+r1_lane_launches.csv (launch list of bench.py's timed region), r1_lane_kernel_ncu_raw.csv (selected raw metrics
+of one full ncu capture), dram_traffic.json (bytes per stream-sample), r1_bench.json (the bench line)."""
+import csv, io, json, shutil, subprocess, sys
+B, N = 75776, 32768
+rows = list(csv.reader(l for l in open('gpurun_out/r1_lane_launches.csv') if not l.startswith('==')))
+hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+bench_ms = json.load(open('gpurun_out/bench_line.json'))["ms_per_step"]
+with open('profiles/r1_lane_launches.csv', 'w') as f:
+    f.write('''# ncu launch list of bench.py's timed region, round 1, lane kernel (bench default)
+# command: ncu --nvtx --nvtx-include "bench_timed/" --metrics gpu__time_duration.sum --clock-control none --csv \\
+#          python bench.py --steps 3 --warmup 1 --no-e2e --no-cpu      (75776 streams x 32768 samples, QPSK 72k s16 RRC-32 x5)
+# Every kernel launched between the two timing events is listed; the only other work in the region is a
+# device-to-device copy of the power-on states + two memsets per step (lrpt_reset_async), which are not kernels.
+# => lrpt::demod_lane_kernel is 100 %% of the kernel time of a step; bench.py's CUDA-event ms_per_step for the same
+#    configuration was %.2f ms (profiles/r1_bench.json), matching these per-launch durations.
+id,kernel,block,grid,gpu__time_duration_ns
+''' % bench_ms)
+    for r in rows[1:]:
+        f.write("%s,%s,%s,%s,%s\n" % (r[ix["ID"]], r[ix["Kernel Name"]].replace(",", ""), r[ix["Block Size"]].replace(",", ""),
+                                      r[ix["Grid Size"]].replace(",", ""), r[ix["Metric Value"]]))
+rep = 'gpurun_out/lane_w16.ncu-rep'
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
+with open('profiles/r1_lane_kernel_ncu_raw.csv', 'w') as f:
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:demod_lane -s 1 -c 1 python tools/prof_one.py 75776 32768 32 5 0 lane\n")
+    f.write("# one launch of lrpt::demod_lane_kernel<false,16,false>: 75776 streams x 32768 samples, QPSK 72k s16 RRC-32 x5 (selected raw metrics)\n")
+    f.write("metric,unit,value\n")
+    for i, h in enumerate(hdr):
+        if h in want:
+            f.write("%s,%s,%s\n" % (h, units[i], vals[i].replace(',', '')))
+d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
+scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+rd = float(d["dram__bytes_read.sum"])*scale[u["dram__bytes_read.sum"]]
+wr = float(d["dram__bytes_write.sum"])*scale[u["dram__bytes_write.sum"]]
+j = json.load(open('profiles/dram_traffic.json'))
+j["c1"] = {"bytes_per_stream_sample": (rd + wr)/(B*N),
+           "source": "profiles/r1_lane_kernel_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum over 75776 streams x 32768 samples (lane kernel)",
+           "algorithmic_bytes_per_stream_sample": 4.626068115234375}
+json.dump(j, open('profiles/dram_traffic.json', 'w'), indent=1)
+shutil.copy('gpurun_out/bench_line.json', 'profiles/r1_bench.json')
+print(open('profiles/r1_lane_kernel_ncu_raw.csv').read()); print(j["c1"])
