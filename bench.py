@@ -51,9 +51,11 @@ def parse():
     ap.add_argument("--streams", type=int, default=75776, help="independent streams per GPU (148 SMs x 16 warps x 32 lanes)")
     ap.add_argument("--samples", type=int, default=1 << 15, help="samples per stream per step")
     ap.add_argument("--kernel", default="auto")
-    ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
+    ap.add_argument("--mode", default="batch", choices=["batch", "sharded", "relay"],
                     help="batch: independent streams (exact); sharded: ONE stream of --stream-samples per job, "
-                         "time-sharded over chunks and GPUs (Tier-S, reports eps)")
+                         "time-sharded over chunks and GPUs (Tier-S, reports eps); relay: the batch with its TIME "
+                         "axis split over the GPUs, complete state handed rank to rank over NCCL (exact)")
+    ap.add_argument("--groups", type=int, default=4, help="relay: stream groups travelling down the ranks")
     ap.add_argument("--stream-samples", type=int, default=1 << 30)
     ap.add_argument("--chunk", type=int, default=1 << 18)
     ap.add_argument("--warm", type=int, default=400000)
@@ -271,6 +273,8 @@ def main():
 
     if a.mode == "sharded":
         return bench_sharded(a, cfg, label, rank, world, local, cpu_base)
+    if a.mode == "relay":
+        return bench_relay(a, cfg, label, rank, world, local)
 
     B, N = a.streams, a.samples
     d = Demod(symrate=symrate, oqpsk=oqpsk, bps=bps, rrc_order=order, interp_factor=interp, nstreams=B,
@@ -477,6 +481,102 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_relay(a, cfg, label, rank, world, local):
+    """Exact time-sharding by state relay (meteor_demod_b200/relay.py): every stream is --samples * world
+    long; rank r holds and demodulates samples [r*S, (r+1)*S) of ALL streams, group by group, after
+    receiving each group's states from rank r-1 (NCCL send/recv, nothing else). Weak scaling: a rank's
+    work and memory are fixed, the streams get longer with the ranks."""
+    import torch
+    import torch.distributed as dist
+    from meteor_demod_b200 import relay, synth
+    symrate, oqpsk, bps, order, interp = cfg
+    G, S = a.groups, a.samples
+    per = a.streams // G
+    B = per * G
+    period = synth.baseband(FS, symrate=symrate, oqpsk=bool(oqpsk), periodic=True, seed=3).astype(np.complex64)
+    # one long synthetic batch; every rank keeps only its own time slice resident
+    slices = []
+    for g in range(G):
+        full = synth.device_streams(period, per, S * world, bps=bps, sps=FS / symrate, seed=11 + g, device="cuda")
+        slices.append(full[:, 2 * rank * S: 2 * (rank + 1) * S].contiguous())
+        if g == 0:
+            head = full[0].cpu().numpy() if rank == 0 else None
+        del full
+    kw = dict(symrate=symrate, oqpsk=oqpsk, bps=bps, rrc_order=order, interp_factor=interp)
+    st = torch.cuda.Stream()
+    groups = [relay.GpuGroup(per, device=local, stream=st, **kw) for _ in range(G)]
+    d = dist if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.cuda.stream(st):
+            if rank == 0:
+                for e in groups:
+                    e.reset()
+            return relay.relay(groups, slices, dist=d)
+
+    res = None
+    for _ in range(a.warmup):
+        res = step()
+    barrier()
+    l0 = sum(e.d.launch_count() for e in groups)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with Clocks(local) as clk:
+        barrier()
+        e0.record(st)
+        for _ in range(a.steps):
+            res = step()
+        e1.record(st)
+        barrier()
+    launches = sum(e.d.launch_count() for e in groups) - l0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    # parity on the benchmarked data: stream 0 of group 0, symbols of all ranks in time order, vs the oracle
+    soft0, n0 = res[0]
+    mine = soft0[0, : int(n0[0].item())].contiguous()
+    cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device="cuda")
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(cnts, cnt)
+    else:
+        cnts = [cnt]
+    cap = int(max(int(c.item()) for c in cnts))
+    pad = torch.zeros((cap, 2), dtype=torch.int8, device="cuda")
+    pad[: mine.shape[0]] = mine
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(parts, pad)
+    else:
+        parts = [pad]
+    if rank == 0:
+        from oracle import pyoracle
+        got = np.concatenate([p[: int(c.item())].cpu().numpy() for p, c in zip(parts, cnts)])
+        w = pyoracle.Oracle(symrate=symrate, oqpsk=oqpsk, bps=bps, order=order, interp=interp).process(head, want_float=False)
+        ok = bool(got.shape[0] == w.nsym and np.array_equal(got, w.soft))
+        line = {"metric": "IQ Msamples/s", "value": world * B * S * a.steps / (total_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s; %d streams x %d samples, time axis split over %d rank(s): %d samples per rank, "
+                                       "%d groups of %d streams relayed with their complete state (%d bytes per group and boundary)"
+                                       % (label, B, S * world, world, S, G, per, groups[0].d.states_size()),
+                           "parity": "bit-exact vs strict-IEEE reference (stream 0 checked across all ranks)",
+                           "l2": "inputs (%.1f GB/GPU) larger than L2" % (B * S * (bps // 4) / 1e9)},
+                "kernel": groups[0].d.kernel_name(), "gpu_launches": int(launches), "oracle_check_stream0_all_ranks": ok,
+                "clocks": clk.summary()}
+        print(json.dumps(line))
+    for e in groups:
+        e.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -167,6 +167,17 @@ int  lrpt_export_state(lrpt_demod_t *h, int stream, void *buf, size_t *len);
 int  lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, size_t len);
 
 /*
+ * All streams at once, DEVICE buffers, asynchronous on `cuda_stream` (NULL = the handle's stream): the
+ * rank-to-rank hand-off of a time-sharded batch (sharded.py, relay). Layout of `d_buf`
+ * (lrpt_states_size bytes): nstreams x lrpt_state_t, then nstreams x (taps-1) complex float delay
+ * lines. The bytes can go straight into ncclSend / ncclRecv. Import trusts the buffer (it checks the
+ * header of stream 0 when `check` is non-zero, which costs a synchronisation).
+ */
+size_t lrpt_states_size(const lrpt_demod_t *h);
+int  lrpt_export_states_device(lrpt_demod_t *h, void *d_buf, size_t len, void *cuda_stream);
+int  lrpt_import_states_device(lrpt_demod_t *h, const void *d_buf, size_t len, int check, void *cuda_stream);
+
+/*
  * Snapshot / restore of ALL streams' states on the device (time-shard two-pass scheme, sharded.py).
  * lrpt_restore copies the snapshot back; quarter_turns (host int32[nstreams], may be NULL) then turns
  * every stream's Costas NCO back by that many quarter turns: p_phase -= turns*pi/2 (pll.c:16), which
@@ -193,7 +204,7 @@ unsigned long long lrpt_launch_count(const lrpt_demod_t *h);
 /* FIR outputs the recurrence had to evaluate itself because the speculative FIR warps had not (spec kernel;
  * a cost indicator, never a correctness matter) */
 unsigned long long lrpt_fir_fallbacks(lrpt_demod_t *h);
-/* name of the kernel AUTO resolved to ("simple" | "ws" | "spec") */
+/* name of the kernel AUTO resolved to ("simple" | "ws" | "spec" | "lane") */
 const char *lrpt_kernel_name(const lrpt_demod_t *h);
 const char *lrpt_last_error(const lrpt_demod_t *h);  /* human-readable detail of the last failure */
 const char *lrpt_strerror(int code);

@@ -57,6 +57,9 @@ SYMBOLS = {
     "lrpt_state_size": (C.c_size_t, [C.c_void_p]),
     "lrpt_export_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]),
     "lrpt_import_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "lrpt_states_size": (C.c_size_t, [C.c_void_p]),
+    "lrpt_export_states_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lrpt_import_states_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "lrpt_snapshot": (C.c_int, [C.c_void_p]),
     "lrpt_restore": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lrpt_describe": (C.c_int, [C.POINTER(Params), C.POINTER(State), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

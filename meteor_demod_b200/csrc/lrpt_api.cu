@@ -526,6 +526,41 @@ extern "C" int lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, s
 	return LRPT_OK;
 }
 
+extern "C" size_t lrpt_states_size(const lrpt_demod_t *h)
+{
+	return h ? (size_t)h->p.nstreams*lrpt_state_size(h) : 0;
+}
+
+extern "C" int lrpt_export_states_device(lrpt_demod_t *h, void *d_buf, size_t len, void *cuda_stream)
+{
+	if (!h || !d_buf || len != lrpt_states_size(h)) return LRPT_ERR_ARG;
+	CU(h, cudaSetDevice(h->p.device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+	const size_t ns = (size_t)h->p.nstreams, sb = sizeof(lrpt_state_t)*ns;
+	CU(h, cudaMemcpyAsync(d_buf, h->d_states, sb, cudaMemcpyDeviceToDevice, st));
+	if (h->H > 0)
+		CU(h, cudaMemcpyAsync((char *)d_buf + sb, h->d_hist, sizeof(float2)*(size_t)h->H*ns, cudaMemcpyDeviceToDevice, st));
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_import_states_device(lrpt_demod_t *h, const void *d_buf, size_t len, int check, void *cuda_stream)
+{
+	if (!h || !d_buf || len != lrpt_states_size(h)) return LRPT_ERR_ARG;
+	CU(h, cudaSetDevice(h->p.device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+	if (check) {
+		CU(h, cudaMemcpyAsync(h->h_state, d_buf, sizeof(lrpt_state_t), cudaMemcpyDeviceToHost, st));
+		CU(h, cudaStreamSynchronize(st));
+		if (h->h_state->magic != LRPT_STATE_MAGIC || h->h_state->taps != (uint32_t)h->c.taps)
+			return fail(h, LRPT_ERR_STATE, "state buffer: magic/taps mismatch");
+	}
+	const size_t ns = (size_t)h->p.nstreams, sb = sizeof(lrpt_state_t)*ns;
+	CU(h, cudaMemcpyAsync(h->d_states, d_buf, sb, cudaMemcpyDeviceToDevice, st));
+	if (h->H > 0)
+		CU(h, cudaMemcpyAsync(h->d_hist, (const char *)d_buf + sb, sizeof(float2)*(size_t)h->H*ns, cudaMemcpyDeviceToDevice, st));
+	return LRPT_OK;
+}
+
 extern "C" int lrpt_snapshot(lrpt_demod_t *h)
 {
 	if (!h) return LRPT_ERR_ARG;

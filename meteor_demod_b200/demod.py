@@ -224,6 +224,20 @@ class Demod:
         d["history"] = np.frombuffer(blob[C.sizeof(State):], np.float32).reshape(-1, 2).copy()
         return d
 
+    def states_size(self):
+        return self.lib.lrpt_states_size(self.h)
+
+    def export_states_device(self, buf, stream=None):
+        """All streams' states into a uint8 device tensor of states_size() bytes (async on `stream`)."""
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        self._check(self.lib.lrpt_export_states_device(self.h, buf.data_ptr(), buf.numel() * buf.element_size(), st),
+                    "export_states_device")
+
+    def import_states_device(self, buf, check=True, stream=None):
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        self._check(self.lib.lrpt_import_states_device(self.h, buf.data_ptr(), buf.numel() * buf.element_size(),
+                                                       int(check), st), "import_states_device")
+
     def snapshot(self):
         self._check(self.lib.lrpt_snapshot(self.h), "snapshot")
 
