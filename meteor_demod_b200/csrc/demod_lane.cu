@@ -455,8 +455,20 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 
 		/* window full: the last H samples become the head of the next epoch */
 		if (te + 1 == NT && t + 1 < ntiles) {
-			/* ascending in-place copy towards lower entries: safe when source and destination overlap */
-			for (int j = 0; j < H; j++) col[j*32] = col[(NT*T + j)*32];
+			/* ascending in-place copy towards lower entries, 16 loads then 16 stores at a time (the loads of a
+			 * batch overlap each other): safe when source and destination overlap, because a batch's
+			 * destination lies below every source still to be read (NT*T >= 32 > 15) */
+			const int shift = NT*T;
+			int j = 0;
+#pragma unroll 1
+			for (; j + 16 <= H; j += 16) {
+				elem v[16];
+#pragma unroll
+				for (int u = 0; u < 16; u++) v[u] = col[(shift + j + u)*32];
+#pragma unroll
+				for (int u = 0; u < 16; u++) col[(j + u)*32] = v[u];
+			}
+			for (; j < H; j++) col[j*32] = col[(shift + j)*32];
 			ep0 += NT*T;
 		}
 	}

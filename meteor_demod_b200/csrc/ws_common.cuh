@@ -169,15 +169,16 @@ LRPT_DEV bool nco_to_crossing4(Loop &r, const lrpt_consts_t &c, int n0, int &Q, 
 	const float f = r.t_freq;
 	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
 	float p = r.t_phase;
-	switch (n0 & 3) {                                               /* warp-uniform */
-		case 3: p = __fadd_rn(p, f);
-		case 2: p = __fadd_rn(p, f);
-		case 1: p = __fadd_rn(p, f);
-		default: break;
-	}
-	for (int b = n0 >> 2; b > 0; b--) {
-		p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f);
-	}
+	/* n0 plain adds, n0 warp-uniform: binary decomposition, so that the only control flow is a handful
+	 * of uniform branches around straight-line runs of 16, 8, 4, 2 and 1 adds */
+#define NCO_RUN(N) do { _Pragma("unroll") for (int j_ = 0; j_ < (N); j_++) p = __fadd_rn(p, f); } while (0)
+	for (int b = n0 >> 5; b > 0; b--) NCO_RUN(32);
+	if (n0 & 16) NCO_RUN(16);
+	if (n0 & 8) NCO_RUN(8);
+	if (n0 & 4) NCO_RUN(4);
+	if (n0 & 2) NCO_RUN(2);
+	if (n0 & 1) NCO_RUN(1);
+#undef NCO_RUN
 	const float s0 = __fadd_rn(p, f), s1 = __fadd_rn(s0, f), s2 = __fadd_rn(s1, f), s3 = __fadd_rn(s2, f);
 	const bool c0 = s0 >= thr, c1 = s1 >= thr, c2 = s2 >= thr, c3 = s3 >= thr;
 	if (f > 0.0f && !(p >= thr) && (c0 || c1 || c2 || c3) && Q + n0 + 4 <= Qend) {
