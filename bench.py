@@ -223,6 +223,25 @@ def cpu_reference(cfg, seconds, cores=None):
                          "-march=x86-64-v3 -ftree-vectorize -std=gnu99" if kind == "reference" else "oracle port, strict IEEE")}
 
 
+def bind_to_gpu_cpus(index):
+    """Restrict this process to the CPU cores NVML reports as local to GPU `index`, so that the pinned
+    host buffers of the end-to-end path are first-touched on that GPU's NUMA node (matters with several
+    ranks on a two-socket box). Returns the number of cores bound to, or None when NVML gives nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ main -----------
 
 def main():
@@ -266,6 +285,7 @@ def main():
     import torch.distributed as dist
     from meteor_demod_b200 import Demod, synth
 
+    numa = bind_to_gpu_cpus(local)                          # pinned host buffers land on the GPU's own NUMA node
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the demodulator has no CPU fallback")
     torch.cuda.set_device(local)
@@ -398,7 +418,7 @@ def main():
         traffic = float(tj["bytes_per_stream_sample"]) * B * N
     except Exception:
         pass
-    fir_flops = B * N * 4.0 * (2 * order + 1) * interp                   # all-phase FIR, mul and add counted separately
+    fir_flops = float(counts.sum()) * (2 if oqpsk else 1) * 4.0 * (2 * order + 1)   # one filter_get per (half-)symbol
     line = {"metric": "IQ Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -407,9 +427,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "recurrence/FP32-issue bound, not HBM bound (DESIGN.md section 5); "
-                                 "fp32: %.2f Tinstr/s of all-phase FIR mul+add" % (fir_flops / (kern_ms * 1e-3) / 1e12)},
-            "e2e": e2e}
+                         "note": "instruction-issue bound, not HBM bound (DESIGN.md section 5); the reference's own lazy "
+                                 "FIR (4*taps flops per filter_get) runs at %.2f Tflop/s" % (fir_flops / (kern_ms * 1e-3) / 1e12)},
+            "e2e": e2e, "host_cores_bound_to_gpu_numa_node": numa}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line))
