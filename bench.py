@@ -38,6 +38,9 @@ WORKLOADS = {
     "c2": (80000, 1, 8, 32, 5, "OQPSK 80ksym/s fs=230kS/s u8 RRC-32 x5"),
     "c3": (72000, 0, 16, 64, 8, "QPSK 72ksym/s fs=230kS/s s16 RRC-64 x8"),
 }
+# streams per GPU that fill every SM with as many warps as the lane kernel's shared-memory delay lines allow
+# (148 SMs x W warps x 32 lanes; W = 16 at 65 taps, 11 at 129 taps of 16-bit input)
+DEFAULT_STREAMS = {"c1": 75776, "c2": 75776, "c3": 52096}
 FS = 230000
 
 
@@ -48,7 +51,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=75776, help="independent streams per GPU (148 SMs x 16 warps x 32 lanes)")
+    ap.add_argument("--streams", type=int, default=0, help="independent streams per GPU (default: DEFAULT_STREAMS[workload])")
     ap.add_argument("--samples", type=int, default=1 << 15, help="samples per stream per step")
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--mode", default="batch", choices=["batch", "sharded", "relay"],
@@ -246,6 +249,8 @@ def bind_to_gpu_cpus(index):
 
 def main():
     a = parse()
+    if a.streams <= 0:
+        a.streams = DEFAULT_STREAMS[a.workload]
     symrate, oqpsk, bps, order, interp, label = WORKLOADS[a.workload]
     cfg = (symrate, oqpsk, bps, order, interp)
     rank = int(os.environ.get("RANK", "0"))
@@ -418,6 +423,21 @@ def main():
         traffic = float(tj["bytes_per_stream_sample"]) * B * N
     except Exception:
         pass
+    limiter = None                                          # what ncu says binds the kernel (committed capture)
+    try:
+        prof = {}
+        for ln in open(os.path.join(ROOT, "profiles", "r1_lane_kernel_ncu_raw.csv")):
+            f = ln.strip().split(",")
+            if len(f) == 3 and not ln.startswith("#"):
+                prof[f[0]] = f[2]
+        if a.workload == "c1" and d.kernel_name() == "lane":
+            limiter = {"resource": "warp instruction issue slots",
+                       "issue_active_pct": float(prof["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+                       "fma_pipe_pct": float(prof["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
+                       "alu_pipe_pct": float(prof["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]),
+                       "source": "profiles/r1_lane_kernel_ncu_raw.csv (ncu --set full, same kernel and workload)"}
+    except Exception:
+        pass
     fir_flops = float(counts.sum()) * (2 if oqpsk else 1) * 4.0 * (2 * order + 1)   # one filter_get per (half-)symbol
     line = {"metric": "IQ Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -428,7 +448,8 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "instruction-issue bound, not HBM bound (DESIGN.md section 5); the reference's own lazy "
-                                 "FIR (4*taps flops per filter_get) runs at %.2f Tflop/s" % (fir_flops / (kern_ms * 1e-3) / 1e12)},
+                                 "FIR (4*taps flops per filter_get) runs at %.2f Tflop/s" % (fir_flops / (kern_ms * 1e-3) / 1e12),
+                         "limiter": limiter},
             "e2e": e2e, "host_cores_bound_to_gpu_numa_node": numa}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
