@@ -61,8 +61,12 @@ def parse():
     ap.add_argument("--groups", type=int, default=4, help="relay: stream groups travelling down the ranks")
     ap.add_argument("--stream-samples", type=int, default=1 << 30)
     ap.add_argument("--chunk", type=int, default=1 << 18)
-    ap.add_argument("--warm", type=int, default=400000)
+    ap.add_argument("--warm", type=int, default=0, help="sharded: warm-up samples per chunk (default 150000 with the "
+                    "hand-off scheme, 400000 otherwise)")
+    ap.add_argument("--two-pass", action="store_true", help="sharded: two-pass lock-point alignment instead of hand-off")
     ap.add_argument("--single-pass", action="store_true")
+    ap.add_argument("--handoff", action="store_true",
+                    help="sharded: chunks continue from their predecessor's state (sharded.run_handoff; the default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target CPU work per core for the baseline")
@@ -466,11 +470,15 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
     from meteor_demod_b200 import sharded, synth
     symrate, oqpsk, bps, order, interp = cfg
     N = a.stream_samples
+    a.handoff = not (a.two_pass or a.single_pass)
+    if a.warm <= 0:
+        a.warm = 150000 if a.handoff else 400000
     plan = sharded.Plan(N, a.chunk, a.warm, 8192, interp)
     period = synth.baseband(FS, symrate=symrate, oqpsk=bool(oqpsk), periodic=True, seed=3).astype(np.complex64)
     raw = synth.device_long_stream(period, N, total=plan.padded, bps=bps, sps=FS / symrate)
     kw = dict(chunk=a.chunk, warm=a.warm, overlap=8192, device=local, dist=dist if world > 1 else None,
-              symrate=symrate, bps=bps, rrc_order=order, interp_factor=interp, two_pass=not a.single_pass)
+              symrate=symrate, bps=bps, rrc_order=order, interp_factor=interp, two_pass=not a.single_pass,
+              handoff=a.handoff)
 
     def barrier():
         torch.cuda.synchronize()
@@ -515,7 +523,7 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "%s; ONE stream of %d samples time-sharded: %d chunks of %d, warm-up %d, overlap 8192, %s"
-                           % (label, N, plan.nchunks, a.chunk, a.warm, "single pass" if a.single_pass else "two-pass lock-point alignment"),
+                           % (label, N, plan.nchunks, a.chunk, a.warm, "state hand-off between chunks" if a.handoff else "single pass" if a.single_pass else "two-pass lock-point alignment"),
                            "parity": "Tier-S (statistical): chunk 0 bit-exact, later chunks see tier_s",
                            "l2": "stream (%.1f GB) larger than L2" % (N * (bps // 4) / 1e9)},
                 "gpu_launches": int(launches), "symbols_per_step": int(nsym.item()),

@@ -522,8 +522,10 @@ static size_t ln_warp_smem(int taps, int NT, int bps) { return (size_t)((taps - 
 
 bool lane_supported(const lrpt_consts_t &c)
 {
-	return c.interp >= 1 && c.interp <= LN_MAX_L && c.taps >= 1 && c.taps <= LN_MAX_TAPS &&
-	       (c.bps == 8 || c.bps == 16 || c.bps == 32);
+	if (!(c.interp >= 1 && c.interp <= LN_MAX_L && c.taps >= 1 && c.taps <= LN_MAX_TAPS &&
+	      (c.bps == 8 || c.bps == 16 || c.bps == 32))) return false;
+	/* one warp's delay lines (shortest epoch) + the tap table must fit the 227 KB a CTA can opt into on sm_100 */
+	return ln_fixed_smem(c.taps, c.interp) + ln_warp_smem(c.taps, 1, c.bps) <= (size_t)232448;
 }
 
 template <bool OQ, int BPS> static cudaError_t ln_attr1()

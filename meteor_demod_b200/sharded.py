@@ -49,6 +49,7 @@ class Plan:
     overlap: int       # V: overlap into the successor
     interp: int        # L: timing sub-steps per sample
     nchunks: int = 0
+    cut_shift: int = 0 # samples added to every cut target (hand-off scheme: rows start V samples after their boundary)
 
     def __post_init__(self):
         if self.chunk <= 0 or self.warm < 0 or self.overlap <= 0:
@@ -65,15 +66,15 @@ class Plan:
         """Sub-step index around which chunks c-1 and c are joined: a little INSIDE chunk c's owned region,
         so that both rows have symbols on either side of the cut (in the two-pass scheme row c only starts
         at B_c; a symbol instant falling exactly on B_c is in one row and not the other)."""
-        return (self.boundary(c) + min(64, self.overlap // 4)) * self.interp
+        return (self.boundary(c) + self.cut_shift + min(64, self.overlap // 4)) * self.interp
 
     @property
     def n_main(self):              # samples up to the successor's boundary
         return self.warm + self.chunk
 
     @property
-    def padded(self):              # buffer length that lets every chunk read n_main + overlap samples
-        return (self.nchunks - 1) * self.chunk + self.n_main + self.overlap
+    def padded(self):              # buffer length that lets every chunk read n_main + 2*overlap samples
+        return (self.nchunks - 1) * self.chunk + self.n_main + 2 * self.overlap
 
 
 def rotate_quarter_turns(soft, k):
@@ -300,9 +301,123 @@ class GpuEngine:
         self.d.sync()
         return self._result(p.warm)
 
+    # -- hand-off scheme (run_handoff) -----------------------------------------------------------------
+    def pass_a(self):
+        return self.warm_up()
+
+    def pass_b(self):
+        """From the live state at B_c: owned + overlap samples; every row ends at B_{c+1} + V."""
+        p = self.plan
+        n = p.chunk + p.overlap
+        self.d.process_device(self._view(p.warm, n), self.soft, nsym=self.nsym, nsamples=n)
+        self.d.sync()
+        soft, q, count = self._result(p.warm)
+        return soft.clone(), q, count.clone()
+
+    def pass_c(self):
+        """From the imported states: owned + overlap samples starting V samples after the boundary."""
+        p = self.plan
+        n = p.chunk + p.overlap
+        self.d.process_device(self._view(p.warm + p.overlap, n), self.soft, nsym=self.nsym, nsamples=n)
+        self.d.sync()
+        return self._result(p.warm + p.overlap)
+
+    def export_rows(self):
+        """Complete state of every row as bytes [M, state_size] (lrpt_state_t + delay line per row)."""
+        from ._lib import State
+        import ctypes as C
+        sb = C.sizeof(State)
+        buf = torch.empty(self.d.states_size(), dtype=torch.uint8, device=self.raw.device)
+        self.d.export_states_device(buf)
+        self.d.sync()
+        hb = (buf.numel() - self.M * sb) // self.M
+        return torch.cat((buf[: self.M * sb].view(self.M, sb), buf[self.M * sb:].view(self.M, hb)), dim=1)
+
+    def import_rows(self, rows):
+        from ._lib import State
+        import ctypes as C
+        sb = C.sizeof(State)
+        buf = torch.cat((rows[:, :sb].reshape(-1), rows[:, sb:].reshape(-1))).contiguous()
+        self.d.import_states_device(buf, check=True)
+        self.d.sync()
+
+    @staticmethod
+    def rotate_rows(rows, turns):
+        """Every row's Costas NCO turned back by `turns` quarter turns, exactly as lrpt_restore does:
+        p_phase = (float)((double)p_phase - (turns & 3) * M_PI/2)  (pll.c:16)."""
+        from ._lib import State
+        off = State.p_phase.offset
+        out = rows.clone()
+        ph = out[:, off: off + 4].contiguous().view(torch.float32).reshape(-1)
+        new = (ph.double() - (turns.to(ph.device) & 3).double() * 1.57079632679489661923).float()
+        out[:, off: off + 4] = new.view(-1, 1).view(torch.uint8)
+        return out
+
     def close(self):
         self.d.set_symbol_index_output(None)
         self.d.close()
+
+
+def run_handoff(eng, plan, first_chunk=0, dist=None):
+    """Time-sharding with state hand-off between chunks (Tier-S, same cost as the two-pass scheme, longer
+    effective warm-up): pass A = warm-up W from power-on; pass B = owned + overlap, giving the quadrant
+    scan AND, at its end, the state of every row V samples past its successor's boundary; pass C = every
+    row continues from the state of its PREDECESSOR row (turned to the sequential run's lock point), so
+    the symbols it contributes come from a trajectory with W + C + V samples of history instead of W.
+    The row after chunk 0 inherits the exact sequential state and stays bit-exact as well. Across ranks
+    the predecessor state of a rank's first row arrives from the previous rank (send/recv of one state:
+    NCCL between GPUs); the quadrant scan's exchange is stitch()'s.
+
+    eng: pass_a() -> head symbols of row 0, pass_b()/pass_c() -> (soft, q, count), export_rows() ->
+    [M, R] tensor, import_rows(rows), rotate_rows(rows, turns); eng.M local rows."""
+    import dataclasses
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    M = eng.M
+    if first_chunk == 0 and M < 2 and plan.nchunks > 1:
+        raise ValueError("the rank holding chunk 0 needs at least two chunks")
+    head = eng.pass_a()
+    soft_b, q_b, n_b = eng.pass_b()
+    scan = stitch(soft_b, q_b, n_b, plan, first_chunk=first_chunk, dist=dist)
+    K = chunk_turns(scan, M)
+    turned = eng.rotate_rows(eng.export_rows(), K)
+    incoming = turned[:1].clone()                                   # placeholder for the row that has no predecessor
+    req = None
+    if world > 1:
+        if rank + 1 < world and first_chunk + M < plan.nchunks:
+            req = dist.isend(turned[-1:].contiguous(), rank + 1)
+        if rank > 0:
+            dist.recv(incoming, rank - 1)
+        if req is not None:
+            req.wait()
+    eng.import_rows(torch.cat((incoming, turned[:-1])))
+    soft_c, q_c, n_c = eng.pass_c()
+    shifted = dataclasses.replace(plan, cut_shift=plan.overlap)
+    if first_chunk == 0:
+        if M == 1:                                                  # the whole stream is chunk 0: already exact
+            res = dict(scan)
+            res["soft"] = torch.cat((_as_tensor(head, soft_b.device), soft_b[0, : int(n_b[0].item())]))
+            res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
+            return res
+        # rows 0 and 1 are one exact trajectory: row 0's pass-B symbols, then row 1's pass-C symbols
+        n0, n1 = int(n_b[0].item()), int(n_c[1].item())
+        cap = max(soft_c.shape[1], n0 + n1)
+        soft = torch.zeros((M - 1, cap, 2), dtype=torch.int8, device=soft_c.device)
+        q = torch.zeros((M - 1, cap), dtype=torch.int64, device=soft_c.device)
+        soft[0, :n0], q[0, :n0] = soft_b[0, :n0], q_b[0, :n0]
+        soft[0, n0: n0 + n1], q[0, n0: n0 + n1] = soft_c[1, :n1], q_c[1, :n1]
+        soft[1:, : soft_c.shape[1]], q[1:, : soft_c.shape[1]] = soft_c[2:], q_c[2:]
+        count = torch.cat((torch.tensor([n0 + n1], dtype=torch.int64, device=soft_c.device), n_c[2:]))
+        res = stitch(soft, q, count, shifted, first_chunk=1, dist=dist)
+        res["soft"] = torch.cat((_as_tensor(head, soft.device), res["soft"]))
+    else:
+        res = stitch(soft_c, q_c, n_c, shifted, first_chunk=first_chunk, dist=dist)
+    res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
+    return res
+
+
+def _as_tensor(x, device):
+    return x.to(device) if isinstance(x, torch.Tensor) else torch.from_numpy(x).to(device)
 
 
 class ShardedDemod:
@@ -310,11 +425,11 @@ class ShardedDemod:
     are built once; run() can be called repeatedly, e.g. by bench.py)."""
 
     def __init__(self, raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
-                 interp_factor=5, two_pass=True, **cfg):
+                 interp_factor=5, two_pass=True, handoff=False, **cfg):
         if cfg.get("oqpsk"):
             raise NotImplementedError("time-sharding resolves the k*90 degree ambiguity of QPSK only")
         self.plan = plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
-        self.dist, self.two_pass = dist, two_pass
+        self.dist, self.two_pass, self.handoff = dist, two_pass, handoff
         world = dist.get_world_size() if dist is not None else 1
         rank = dist.get_rank() if dist is not None else 0
         if plan.nchunks < world:
@@ -325,7 +440,9 @@ class ShardedDemod:
     def run(self):
         eng, plan, c0, M = self.eng, self.plan, self.c0, self.c1 - self.c0
         l0 = eng.d.launch_count()
-        if not self.two_pass:
+        if self.handoff:
+            res = run_handoff(eng, plan, first_chunk=c0, dist=self.dist)
+        elif not self.two_pass:
             res = stitch(*eng.run(), plan, first_chunk=c0, dist=self.dist)
         else:
             head = eng.warm_up()

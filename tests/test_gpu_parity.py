@@ -196,6 +196,23 @@ def test_configurations_outside_the_fast_kernel_fall_back_exactly(oracle_mod, li
                   interp_factor=cfg["interp"], kernel="ws")
 
 
+def test_longest_filters_pick_a_kernel_that_fits(oracle_mod, lib):
+    """rrc_order 512 (1025 taps): the lane kernel's shared-memory delay lines fit for 8-bit input but not
+    for float input; AUTO has to notice and stay exact either way."""
+    from meteor_demod_b200 import Demod, synth
+    for bps, served_by in ((8, "lane"), (32, "simple")):
+        cfg = dict(symrate=72000, oqpsk=0, bps=bps, order=512, interp=4)
+        raw = synth.make_raw(6000, bps=bps, seed=4)
+        d = Demod(symrate=72000, oqpsk=0, bps=bps, rrc_order=512, interp_factor=4, kernel="auto")
+        assert d.kernel_name() == served_by
+        soft, n = d.process(raw)
+        o = oracle_mod.Oracle(**cfg)
+        w = o.process(raw)
+        assert n is not None and soft.shape[0] == w.nsym and np.array_equal(soft, w.soft)
+        assert_state_equal(d.state(), o)
+        d.close()
+
+
 def test_long_push_is_split_transparently(lib):
     """More samples than one launch addresses with int32 sub-step indices (2^26): the library cuts the push
     into several launches; the result must equal two half-size pushes (state + append cursor carried)."""

@@ -274,3 +274,116 @@ def test_gpu_sharded_equals_oracle_sharded(single, stream, lib):
     assert out["plan"].nchunks == plan.nchunks and out["launches"] == 1
     assert torch.equal(out["k"].cpu(), res["k"])
     assert np.array_equal(out["soft"].cpu().numpy(), res["soft"].numpy())
+
+
+# ------------------------------------------------------------------ hand-off scheme (run_handoff) --
+
+class OracleEngine:
+    """CPU stand-in for sharded.GpuEngine in run_handoff: one oracle per local chunk; a row of state is a
+    float64 vector (every float32/int field exactly) followed by the delay line."""
+
+    def __init__(self, raw, plan, first_chunk=0, nchunks=None):
+        from oracle import pyoracle
+        self.plan, self.first = plan, first_chunk
+        self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
+        self.pad = np.zeros(2 * plan.padded, raw.dtype)
+        self.pad[: raw.size] = raw
+        self.o = [pyoracle.Oracle(**CFG) for _ in range(self.M)]
+        self.keys = sorted(self.o[0].state())
+
+    def _run(self, offset, n, want_q=True):
+        L = self.plan.interp
+        outs = []
+        for i, o in enumerate(self.o):
+            s0 = self.plan.start(self.first + i) + offset
+            w = o.process(self.pad[2 * s0: 2 * (s0 + n)], want_float=False, want_substep=True)
+            outs.append((w.soft, w.q + s0 * L))
+        return outs
+
+    def pass_a(self):
+        outs = self._run(0, self.plan.warm)
+        return outs[0][0]
+
+    def pass_b(self):
+        return _rows(self._run(self.plan.warm, self.plan.chunk + self.plan.overlap))
+
+    def pass_c(self):
+        return _rows(self._run(self.plan.warm + self.plan.overlap, self.plan.chunk + self.plan.overlap))
+
+    def export_rows(self):
+        rows = [np.concatenate([[float(o.state()[k]) for k in self.keys], o.history().reshape(-1).astype(np.float64)])
+                for o in self.o]
+        return torch.from_numpy(np.stack(rows))
+
+    def import_rows(self, rows):
+        for o, row in zip(self.o, rows.numpy()):
+            cur = o.state()
+            o.set_state(**{k: type(cur[k])(v) for k, v in zip(self.keys, row[: len(self.keys)])})
+            o.set_history(row[len(self.keys):].astype(np.float32))
+
+    def rotate_rows(self, rows, turns):
+        out = rows.clone()
+        j = self.keys.index("p_phase")
+        ph = out[:, j].to(torch.float32)
+        out[:, j] = (ph.double() - (turns & 3).double() * 1.57079632679489661923).float().double()
+        return out
+
+
+def test_handoff_scheme_on_the_oracle(stream):
+    """run_handoff with the oracle as the engine: same symbol count as the sequential run, chunks 0 AND 1
+    bit-exact (chunk 1 inherits the exact state), every final boundary already aligned, and an eps at the
+    level of the two-pass scheme with a shorter warm-up (160k instead of 400k samples)."""
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    res = sharded.run_handoff(OracleEngine(stream, plan), plan)
+    seq = sequential(stream)
+    got = res["soft"].numpy()
+    rep = tier_s_report(got, seq)
+    assert rep["n_stitched"] == rep["n_seq"]
+    assert res["k"].tolist() == [0] * (plan.nchunks - 2)         # rows 0+1 are one row in the final table
+    n01 = int(plan.boundary(2) * 72000 / 230000) - 16
+    assert np.array_equal(got[:n01], seq[:n01])                   # chunk 0 and chunk 1: exact
+    assert float(res["agreement"].min()) > 0.995
+    assert rep["frac_gt1"] < 0.006, rep
+    print("hand-off Tier-S report:", rep, "first-pass K:", res["first_pass"]["K"].tolist())
+
+
+def _handoff_rank_main(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from meteor_demod_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    raw = make_stream()
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
+    res = sharded.run_handoff(OracleEngine(raw, plan, c0, c1 - c0), plan, first_chunk=c0, dist=dist)
+    np.save(os.path.join(out_dir, "hpart%d.npy" % rank), res["soft"].numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_handoff_equals_single_process(stream, tmp_path):
+    """The hand-off scheme over 2 ranks (gloo): the predecessor state of rank 1's first chunk travels by
+    send/recv; the concatenated output equals the single-process run."""
+    import torch.multiprocessing as mp
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    want = sharded.run_handoff(OracleEngine(stream, plan), plan)["soft"].numpy()
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_handoff_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.concatenate([np.load(tmp_path / ("hpart%d.npy" % r)) for r in range(2)])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_handoff_equals_oracle_handoff(stream, lib):
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    want = sharded.run_handoff(OracleEngine(stream, plan), plan)
+    raw = torch.zeros(2 * plan.padded, dtype=torch.int16, device="cuda")
+    raw[: stream.size] = torch.from_numpy(stream).cuda()
+    out = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
+                                rrc_order=32, interp_factor=5, handoff=True)
+    assert torch.equal(out["first_pass"]["K"].cpu(), want["first_pass"]["K"])
+    assert np.array_equal(out["soft"].cpu().numpy(), want["soft"].numpy())
