@@ -139,7 +139,6 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 			const int slot = t % S;
 			mbar_wait(&full[slot], (unsigned)(t/S) & 1u);
 			{
-				const int q0 = t*T*L;
 				const int q1 = min((t + 1)*T, a.nsamples)*L;
 				const float2 *tc = my_cand + slot*KM*NC;
 				const int *tk = my_ck + slot*KM;
