@@ -34,7 +34,10 @@
 
 namespace lrpt {
 
-constexpr int LN_T         = 16;   /* samples per tile (per lane)                          */
+#ifndef LRPT_LANE_T
+#define LRPT_LANE_T 16
+#endif
+constexpr int LN_T         = LRPT_LANE_T;   /* samples per tile (per lane) */
 constexpr int LN_MAX_WARPS = 16;   /* warps per CTA = 512 streams                          */
 constexpr int LN_MAX_TAPS  = 1025;
 constexpr int LN_MAX_L     = 8;

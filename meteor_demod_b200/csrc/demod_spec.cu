@@ -31,6 +31,9 @@ constexpr int SP_KMAX   = 12;     /* predicted events per stream and tile       
 constexpr int SP_MAX_G  = 32;     /* streams per CTA                                 */
 constexpr int SP_MAX_TAPS = 257;
 constexpr int SP_MAX_L  = 8;
+constexpr int SP_CSTR   = SP_SLOTS*SP_KMAX*SP_NC + 1;   /* float2 per stream of candidates: 146 words, so that
+                                                           the 32 recurrence lanes hit different banks */
+constexpr int SP_KSTR   = SP_SLOTS*SP_KMAX + 1;         /* ints per stream of centre sub-steps (odd)     */
 constexpr int SP_PAD    = 4;      /* window guard entries (reads up to 2 samples past a tile, 1 before) */
 
 struct SpArgs {
@@ -95,7 +98,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 	float4 *pubs = reinterpret_cast<float4 *>(hT + ((taps*LP + 3) & ~3));     /* [G] published timing state */
 	float2 *wins = reinterpret_cast<float2 *>(pubs + a.G);          /* [G][wstride] delay-line windows */
 	float2 *cand = wins + (size_t)a.G*wstride;                      /* [G][S][KM][NC] candidate FIR outputs */
-	int    *cks  = reinterpret_cast<int *>(cand + (size_t)a.G*S*KM*NC);       /* [G][S][KM] their centre sub-steps */
+	int    *cks  = reinterpret_cast<int *>(cand + (size_t)a.G*SP_CSTR);       /* [G][S][KM] their centre sub-steps */
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < S; s++) { mbar_init(&full[s], P); mbar_init(&empty[s], 1); }
@@ -132,8 +135,8 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 		int Q = 0;
 		bool have_x = false; int Qx = 0, half = 0;
 		const float2 *my_win = wins + (size_t)lane*wstride + 1;     /* +1: guard entry in front */
-		const float2 *my_cand = cand + (size_t)lane*S*KM*NC;
-		const int *my_ck = cks + (size_t)lane*S*KM;
+		const float2 *my_cand = cand + (size_t)lane*SP_CSTR;
+		const int *my_ck = cks + (size_t)lane*SP_KSTR;
 
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
@@ -142,7 +145,13 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 				const int q1 = min((t + 1)*T, a.nsamples)*L;
 				const float2 *tc = my_cand + slot*KM*NC;
 				const int *tk = my_ck + slot*KM;
-				int ks = 0;                                         /* candidate events are stored in time order */
+				/* candidate events are stored in time order; the entry the next event is expected to hit is
+				 * fetched ahead (centre sub-step + its three FIR outputs), so that the look-up costs the
+				 * recurrence no shared-memory round trip once the crossing is known */
+				int ks = 0;
+				int ckn = -0x40000000;
+				float2 c0 = make_float2(0.f, 0.f), c1 = c0, c2 = c0;
+				if (active) { ckn = tk[0]; c0 = tc[0]; c1 = tc[1]; c2 = tc[2]; }
 				while (true) {
 					if (active && !have_x && Q < q1)
 						have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
@@ -151,11 +160,19 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 					if (!__any_sync(0xffffffffu, ready)) break;
 					if (ready) {
 						/* filter_get(flt, i) for sub-step Qx: from the candidates, or evaluated here */
-						while (ks < KM - 1 && tk[ks] + 1 < Qx) ks++;
-						const int d = Qx - tk[ks] + 1;
+						while (ks < KM - 1 && ckn + 1 < Qx) {
+							ks++;
+							ckn = tk[ks]; c0 = tc[ks*NC]; c1 = tc[ks*NC + 1]; c2 = tc[ks*NC + 2];
+						}
+						const int d = Qx - ckn + 1;
 						float2 y;
-						if (d >= 0 && d < NC) y = tc[ks*NC + d];
-						else {
+						if (d >= 0 && d < NC) {
+							y = (d == 0) ? c0 : (d == 1) ? c1 : c2;
+							if (ks < KM - 1) {                               /* the next event will look at the next entry */
+								ks++;
+								ckn = tk[ks]; c0 = tc[ks*NC]; c1 = tc[ks*NC + 1]; c2 = tc[ks*NC + 2];
+							} else ckn = -0x40000000;
+						} else {
 							const int n = Qx/L, i = Qx - n*L;
 							y = fir_single<LP>(my_win + (t % NT)*T + (n - t*T), hT, taps, L - 1 - i);
 							misses++;
@@ -262,7 +279,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 					const int cc = Qp + (int)ceilf((thr + E*(m0 - 1.0f + (float)k) - ph)*inv);
 					if (cm >= q0 - 1 && cc >= q0 - 1 && cc <= q1) ck = cc;
 				}
-				cks[((size_t)g*S + slot)*KM + k] = ck;
+				cks[(size_t)g*SP_KSTR + slot*KM + k] = ck;
 				if (ck < 0) continue;
 				/* candidates: sub-steps ck-1, ck, ck+1 (those inside [q0,q1)); sample of the first one = n0 */
 				const int qa = ck - 1;
@@ -321,7 +338,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 						}
 					}
 				}
-				float2 *o = cand + (((size_t)g*S + slot)*KM + k)*NC;
+				float2 *o = cand + (size_t)g*SP_CSTR + (slot*KM + k)*NC;
 #pragma unroll
 				for (int d = 0; d < NC; d++) if (use[d]) o[d] = make_float2(ar[d], ai[d]);
 			}
@@ -378,7 +395,7 @@ static size_t sp_stream_smem(int taps, int T)
 {
 	const int win = (taps - 1) + sp_nt(taps, T)*T;
 	return sizeof(float4) + (size_t)(win + SP_PAD)*sizeof(float2) +
-	       (size_t)SP_SLOTS*SP_KMAX*SP_NC*sizeof(float2) + (size_t)SP_SLOTS*SP_KMAX*sizeof(int);
+	       (size_t)SP_CSTR*sizeof(float2) + (size_t)SP_KSTR*sizeof(int);
 }
 
 bool spec_supported(const lrpt_consts_t &c)
