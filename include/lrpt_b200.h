@@ -186,6 +186,32 @@ int  lrpt_import_states_device(lrpt_demod_t *h, const void *d_buf, size_t len, i
 int  lrpt_snapshot(lrpt_demod_t *h);
 int  lrpt_restore(lrpt_demod_t *h, const int32_t *quarter_turns);
 
+/* ---- joining the chunks of one time-sharded stream (device buffers) ----------
+ * No counterpart in the reference (one sequential stream, demod.c:24-48). Rows = consecutive chunks of
+ * ONE stream demodulated as the streams of a batch (lrpt_process_batch_device with a raw_stride of one
+ * chunk), with the symbol index side output: d_q[r][i] = sub-step of symbol i counted from the row's
+ * first sample, ascending; d_base[r] makes it absolute in the stream; d_count[r] symbols are valid.
+ * Strides in bytes. All four are asynchronous on `cuda_stream` and need no handle. */
+/* boundary b = rows (b | b+1), b < nrows-1: cut point mid-way between the two symbols of row b around
+ * d_target[b] (absolute sub-step), first paired symbol in either row, pairs available */
+int  lrpt_shard_find_cuts_device(const uint32_t *d_q, size_t q_stride, const int32_t *d_count, const int64_t *d_base,
+                                 int nrows, const int64_t *d_target, int64_t *d_cut, int32_t *d_ia, int32_t *d_ib,
+                                 int32_t *d_navail, void *cuda_stream);
+/* per boundary: quarter turns k (0..3) that map row b+1 onto row b -- a QPSK Costas loop locks with a
+ * k*90 degree ambiguity (pll.c:143-152) -- from exact integer correlations of `npairs` paired symbols,
+ * and the number of pairs whose hard decisions agree under k with instants at most 2 sub-steps apart */
+int  lrpt_shard_quadrants_device(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride,
+                                 const int64_t *d_base, int nrows, const int32_t *d_ia, const int32_t *d_ib, int npairs,
+                                 int32_t *d_k, int32_t *d_same, void *cuda_stream);
+/* per row: the run of symbols with d_lo[r] < absolute sub-step <= d_hi[r] (INT64_MAX = to the end) */
+int  lrpt_shard_ranges_device(const uint32_t *d_q, size_t q_stride, const int32_t *d_count, const int64_t *d_base, int nrows,
+                              const int64_t *d_lo, const int64_t *d_hi, int32_t *d_start, int32_t *d_len, void *cuda_stream);
+/* d_out[d_off[r] + j] = row r's symbol d_start[r] + j turned by d_turns[r] quarter turns ((I,Q) -> (-Q,I)
+ * each; exact on int8 pairs), j < d_len[r] <= max_len; d_off in symbols */
+int  lrpt_shard_gather_device(const int8_t *d_soft, size_t soft_stride, int nrows, size_t max_len, const int32_t *d_start,
+                              const int32_t *d_len, const int64_t *d_off, const int32_t *d_turns, int8_t *d_out,
+                              void *cuda_stream);
+
 /* ---- introspection -------------------------------------------------------------- */
 /*
  * Host-only (needs no CUDA device): what lrpt_create derives from `p`, exactly as

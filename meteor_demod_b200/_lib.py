@@ -62,6 +62,14 @@ SYMBOLS = {
     "lrpt_import_states_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "lrpt_snapshot": (C.c_int, [C.c_void_p]),
     "lrpt_restore": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lrpt_shard_find_cuts_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lrpt_shard_quadrants_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lrpt_shard_ranges_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lrpt_shard_gather_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrpt_describe": (C.c_int, [C.POINTER(Params), C.POINTER(State), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lrpt_get_taps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lrpt_get_tanh_lut": (C.c_int, [C.c_void_p, C.c_void_p]),

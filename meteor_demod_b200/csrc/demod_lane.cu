@@ -177,6 +177,22 @@ template <> struct RawT<32> {
 	LRPT_DEV static elem zero() { return make_float2(0.f, 0.f); }
 };
 
+/* What the window holds: the raw element (WF = false: smallest footprint, converted at every tap)
+ * or the float pair it converts to (WF = true: converted once per sample when its tile is appended,
+ * 8 bytes per entry, so fewer warps fit but a tap costs three instructions less). */
+template <int BPS, bool WF> struct WinT {
+	typedef RawT<BPS> W;                          /* format the FIR reads */
+	typedef typename RawT<BPS>::elem elem;
+	static constexpr int WBPS = BPS;
+	LRPT_DEV static elem from_raw(typename RawT<BPS>::elem e) { return e; }
+};
+template <int BPS> struct WinT<BPS, true> {
+	typedef RawT<32> W;
+	typedef float2 elem;
+	static constexpr int WBPS = 32;
+	LRPT_DEV static elem from_raw(typename RawT<BPS>::elem e) { return RawT<BPS>::cvt(e); }
+};
+
 /* One FULL tile (LN_T samples starting at s0) of a lane's row into registers. */
 template <int BPS>
 LRPT_DEV void tile_load(const uint8_t *row, int s0, uint4 (&pf)[RawT<BPS>::NV])
@@ -188,18 +204,18 @@ LRPT_DEV void tile_load(const uint8_t *row, int s0, uint4 (&pf)[RawT<BPS>::NV])
 }
 
 /* The last, partial tile goes from global memory to the window element by element. */
-template <int BPS>
-LRPT_DEV void tile_copy_partial(typename RawT<BPS>::elem *col, int e0, const uint8_t *row, int s0, int nsamples)
+template <int BPS, bool WF>
+LRPT_DEV void tile_copy_partial(typename WinT<BPS, WF>::elem *col, int e0, const uint8_t *row, int s0, int nsamples)
 {
 	typedef RawT<BPS> R;
 #pragma unroll 1
 	for (int i = 0; i < LN_T; i++)
-		col[(e0 + i)*32] = (s0 + i < nsamples) ? R::load1(row, s0 + i) : R::zero();
+		col[(e0 + i)*32] = WinT<BPS, WF>::from_raw((s0 + i < nsamples) ? R::load1(row, s0 + i) : R::zero());
 }
 
 /* Registers -> window entries [e0, e0+LN_T) of this lane's column. */
-template <int BPS>
-LRPT_DEV void tile_store(typename RawT<BPS>::elem *col, int e0, const uint4 (&pf)[RawT<BPS>::NV])
+template <int BPS, bool WF>
+LRPT_DEV void tile_store(typename WinT<BPS, WF>::elem *col, int e0, const uint4 (&pf)[RawT<BPS>::NV])
 {
 	typedef RawT<BPS> R;
 	constexpr int PER = 16/sizeof(typename R::elem);
@@ -208,7 +224,7 @@ LRPT_DEV void tile_store(typename RawT<BPS>::elem *col, int e0, const uint4 (&pf
 		typename R::elem e[PER];
 		R::unpack(pf[j], e);
 #pragma unroll
-		for (int i = 0; i < PER; i++) col[(e0 + j*PER + i)*32] = e[i];
+		for (int i = 0; i < PER; i++) col[(e0 + j*PER + i)*32] = WinT<BPS, WF>::from_raw(e[i]);
 	}
 }
 
@@ -311,12 +327,15 @@ LRPT_DEV float2 fir_lazy_with_deferred(const typename RawT<BPS>::elem *__restric
 
 /* ------------------------------------------------------------- kernel ------ */
 
-template <bool OQ, int BPS, bool AUX>
+template <bool OQ, int BPS, bool AUX, bool WF>
 __global__ void __launch_bounds__(32*LN_MAX_WARPS, 1)
 demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 {
 	typedef RawT<BPS> R;
-	typedef typename R::elem elem;
+	typedef WinT<BPS, WF> WT;
+	typedef typename WT::W WR;                                      /* the window's format */
+	typedef typename WT::elem elem;
+	constexpr int WBPS = WT::WBPS;
 	constexpr int T = LN_T;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -362,7 +381,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	/* prologue: delay line (taps-1 samples, oldest first) at entries [0,H), tile 0 behind it */
 	{
 		const float2 *hs = a.hist + (size_t)(a.first_stream + lrow)*H;
-		for (int j = 0; j < H; j++) col[j*32] = R::from_float(hs[j]);
+		for (int j = 0; j < H; j++) col[j*32] = WR::from_float(hs[j]);
 	}
 	uint4 pf[R::NV];
 	if (T <= a.nsamples) tile_load<BPS>(row, 0, pf);
@@ -384,8 +403,8 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	for (int t = 0; t < ntiles; t++) {
 		/* append tile t; start the loads of tile t+1 */
 		const int te = t - (ep0/T);
-		if ((t + 1)*T <= a.nsamples) tile_store<BPS>(col, H + te*T, pf);
-		else tile_copy_partial<BPS>(col, H + te*T, row, t*T, a.nsamples);
+		if ((t + 1)*T <= a.nsamples) tile_store<BPS, WF>(col, H + te*T, pf);
+		else tile_copy_partial<BPS, WF>(col, H + te*T, row, t*T, a.nsamples);
 		if ((t + 2)*T <= a.nsamples) tile_load<BPS>(row, (t + 1)*T, pf);
 		__syncwarp();
 
@@ -409,7 +428,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				const float s_gain = r.gain, s_pp = r.p_phase, s_pf = r.p_freq, s_pe = r.p_err;
 				const int s_lk = r.locked, s_lo = r.locked_once, s_ud = r.updown;
 				Osc next; bool ok;
-				const float2 y = fir_lazy_with_deferred<BPS, OQ>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one,
+				const float2 y = fir_lazy_with_deferred<WBPS, OQ>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one,
 				                                                 r, c, lut, pd, next, ok);
 				if (!(ok && pend)) {                                 /* rare: nothing was outstanding (first event of the
 				                                                        launch), or a shortcut was not provably exact */
@@ -432,7 +451,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				step_critical<OQ>(r, c, half, y.x, y.y, osc.s, osc.co, pd);
 				pend = true; pd_q = Qx;
 #else
-				const float2 y = fir_lazy<BPS>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one);
+				const float2 y = fir_lazy<WBPS>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one);
 				const Loop saved = r;
 				float ore, oim; bool emitted; Osc next;
 				if (!symbol_fast_osc<OQ>(r, c, lut, half, y.x, y.y, osc, ore, oim, emitted, next)) {
@@ -497,7 +516,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 		float2 *hs = a.hist + (size_t)sid*H;
 		for (int j = 0; j < H; j++) {
 			const int m = a.nsamples - H + j;                       /* may be negative: still in the old history */
-			hs[j] = R::cvt(col[(m - ep0 + H)*32]);
+			hs[j] = WR::cvt(col[(m - ep0 + H)*32]);
 		}
 		loop_store(r, a.states[sid]);
 		a.states[sid].nsamples += a.nsamples;
@@ -533,9 +552,13 @@ bool lane_supported(const lrpt_consts_t &c)
 
 template <bool OQ, int BPS> static cudaError_t ln_attr1()
 {
-	cudaError_t e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	cudaError_t e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
 	if (e) return e;
-	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	if (e || BPS == 32) return e;
+	e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false, BPS != 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	if (e) return e;
+	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true, BPS != 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
 }
 
 cudaError_t lane_prepare(int device)
@@ -548,40 +571,64 @@ cudaError_t lane_prepare(int device)
 	return cudaSuccess;
 }
 
-template <bool OQ> static void ln_launch1(const lrpt_consts_t &c, const LaneArgs &w, int blocks, size_t smem, cudaStream_t st)
+template <bool OQ> static void ln_launch1(const lrpt_consts_t &c, const LaneArgs &w, int blocks, size_t smem, cudaStream_t st, bool wf)
 {
 	const int threads = 32*w.W;
 	const bool aux = w.symf || w.symq;                              /* optional float / index side outputs */
-#define LN_GO(B) do { if (aux) demod_lane_kernel<OQ, B, true><<<blocks, threads, smem, st>>>(c, w); \
-                      else     demod_lane_kernel<OQ, B, false><<<blocks, threads, smem, st>>>(c, w); } while (0)
-	if (c.bps == 16)     LN_GO(16);
-	else if (c.bps == 8) LN_GO(8);
-	else                 LN_GO(32);
+#define LN_GO(B, F) do { if (aux) demod_lane_kernel<OQ, B, true, F><<<blocks, threads, smem, st>>>(c, w); \
+                         else     demod_lane_kernel<OQ, B, false, F><<<blocks, threads, smem, st>>>(c, w); } while (0)
+	if (c.bps == 16)     { if (wf) LN_GO(16, true); else LN_GO(16, false); }
+	else if (c.bps == 8) { if (wf) LN_GO(8, true);  else LN_GO(8, false); }
+	else                 LN_GO(32, false);
 #undef LN_GO
+}
+
+/* Warps per CTA and tiles per window epoch for `nwarps` warps of streams and a window entry of wbps/4
+ * bytes: spread the batch over every SM first, then stack warps (one CTA per SM). The epoch is at
+ * least 2 tiles (the head move is an in-place ascending copy, so it may overlap its source) and as
+ * long as shared memory allows, which amortises that move. false: one warp does not fit. */
+static bool ln_plan(int nwarps, int taps, int L, int wbps, int &W, int &NT)
+{
+	const size_t fixed = ln_fixed_smem(taps, L), lim = (size_t)ln_max_smem;
+	W = std::max(1, std::min((nwarps + ln_num_sms - 1)/ln_num_sms, LN_MAX_WARPS));
+	NT = 2;
+	while (W > 1 && fixed + W*ln_warp_smem(taps, NT, wbps) > lim) W--;
+	if (fixed + W*ln_warp_smem(taps, NT, wbps) > lim) NT = 1;
+	if (fixed + W*ln_warp_smem(taps, NT, wbps) > lim) return false;
+	/* level the waves when shared memory caps W */
+	const int per_wave = ln_num_sms*W;
+	const int waves = (nwarps + per_wave - 1)/per_wave;
+	W = std::max(1, std::min(W, (nwarps + waves*ln_num_sms - 1)/(waves*ln_num_sms)));
+	while (NT < 16 && fixed + W*ln_warp_smem(taps, NT + 1, wbps) <= lim) NT++;
+	return true;
+}
+
+/* Window format for a launch. Float pairs cost three instructions less per tap but twice (s16) or four
+ * times (u8) the shared memory; measured (tools/ab_wf.py, B200): +2..10 % when the same number of warps
+ * per SM fits either way, -18 % when the float window halves them. So: float pairs exactly when they
+ * do not cost a warp. LRPT_LANE_WF=0/1 overrides (A/B runs, tests). */
+static bool ln_float_window(const lrpt_consts_t &c, int nwarps)
+{
+	if (c.bps == 32) return false;
+	if (const char *e = getenv("LRPT_LANE_WF")) return atoi(e) != 0;
+	int Wr, NTr, Wf, NTf;
+	if (!ln_plan(nwarps, c.taps, c.interp, c.bps, Wr, NTr) || !ln_plan(nwarps, c.taps, c.interp, 32, Wf, NTf)) return false;
+	return Wf == Wr && NTf >= 2;
 }
 
 cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 {
 	const lrpt_consts_t &c = *a.c;
 	const int L = c.interp, taps = c.taps;
-	const size_t fixed = ln_fixed_smem(taps, L);
-	/* warps per CTA: spread the batch over every SM first, then stack warps (one CTA per SM). The
-	 * window epoch is at least 2 tiles (the head move is an in-place ascending copy, so it may
-	 * overlap its source) and as long as shared memory allows, which amortises that move. */
 	const int nwarps = (a.nstreams + 31)/32;
-	int W = std::max(1, std::min((nwarps + ln_num_sms - 1)/ln_num_sms, LN_MAX_WARPS));
-	int NT = 2;
-	while (W > 1 && fixed + W*ln_warp_smem(taps, NT, c.bps) > (size_t)ln_max_smem) W--;
-	if (fixed + W*ln_warp_smem(taps, NT, c.bps) > (size_t)ln_max_smem) NT = 1;
-	if (fixed + W*ln_warp_smem(taps, NT, c.bps) > (size_t)ln_max_smem) return cudaErrorInvalidConfiguration;
-	/* level the waves when shared memory caps W */
-	const int per_wave = ln_num_sms*W;
-	const int waves = (nwarps + per_wave - 1)/per_wave;
-	W = std::max(1, std::min(W, (nwarps + waves*ln_num_sms - 1)/(waves*ln_num_sms)));
-	while (NT < 16 && fixed + W*ln_warp_smem(taps, NT + 1, c.bps) <= (size_t)ln_max_smem) NT++;
+	const bool wf = ln_float_window(c, nwarps);
+	const int wbps = wf ? 32 : c.bps;                               /* window entry: wbps/4 bytes */
+	const size_t fixed = ln_fixed_smem(taps, L);
+	int W, NT;
+	if (!ln_plan(nwarps, taps, L, wbps, W, NT)) return cudaErrorInvalidConfiguration;
 	const int blocks = (nwarps + W - 1)/W;
-	const size_t smem = fixed + W*ln_warp_smem(taps, NT, c.bps);
-	if (getenv("LRPT_LANE_DEBUG")) fprintf(stderr, "lane: streams %d W %d NT %d blocks %d smem %zu\n", a.nstreams, W, NT, blocks, smem);
+	const size_t smem = fixed + W*ln_warp_smem(taps, NT, wbps);
+	if (getenv("LRPT_LANE_DEBUG")) fprintf(stderr, "lane: streams %d W %d NT %d blocks %d smem %zu wf %d\n", a.nstreams, W, NT, blocks, smem, (int)wf);
 
 	int n = 0;
 	size_t done = 0;
@@ -606,8 +653,8 @@ cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 		w.div_magic = (65536 + L - 1)/L;
 		for (int x = 0; x < LN_T*L; x++)
 			if (((x*w.div_magic) >> 16) != x/L) return cudaErrorInvalidConfiguration;
-		if (c.oqpsk) ln_launch1<true>(c, w, blocks, smem, st);
-		else         ln_launch1<false>(c, w, blocks, smem, st);
+		if (c.oqpsk) ln_launch1<true>(c, w, blocks, smem, st, wf);
+		else         ln_launch1<false>(c, w, blocks, smem, st, wf);
 		n++;
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { if (launches) *launches = n; return e; }

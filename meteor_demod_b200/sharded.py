@@ -34,11 +34,37 @@ Only host logic lives here (torch tensor ops for the index arithmetic, torch.dis
 exchange). Demodulation is `GpuEngine` (liblrpt_b200.so); the tests feed `stitch` with chunks
 demodulated by the CPU oracle to check the logic without a GPU, including a 2-rank gloo run.
 """
+import ctypes as C
 import math
 from dataclasses import dataclass
 
 import numpy as np
 import torch
+
+
+def _on_device(soft, q, base):
+    """Rows as the GPU engine leaves them: int32 row-local sub-step indices + a base per row, on the
+    device. Those are joined by the library's stitch kernels (csrc/shard_stitch.cu); anything else (CPU
+    tensors in the tests, small int64 tables) by the torch ops below -- same arithmetic."""
+    return soft.is_cuda and q.dtype == torch.int32 and base is not None
+
+
+def _lib_call(name, dev, *args):
+    from ._lib import LrptError, load
+    with torch.cuda.device(dev):
+        rc = getattr(load(), name)(*args, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc:
+        raise LrptError(rc, name)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _abs_row(q, base, r):
+    """Absolute sub-step indices of row r, int64."""
+    row = q[r].to(torch.int64)
+    return row if base is None else row + base[r]
 
 
 @dataclass
@@ -99,7 +125,7 @@ def _first_at_or_after(q, count, target):
     return torch.searchsorted(qm, target[:, None].contiguous()).squeeze(1)
 
 
-def boundary_quadrants(soft, q, count, Bq, npairs=None):
+def boundary_quadrants(soft, q, count, Bq, npairs=None, base=None):
     """Rows are consecutive chunks. For every boundary (row c-1 | row c) at sub-step Bq[c-1], pair the
     overlap symbols of the two rows and find the quarter-turn count k mapping row c onto row c-1.
 
@@ -112,6 +138,23 @@ def boundary_quadrants(soft, q, count, Bq, npairs=None):
         z = torch.zeros(0, dtype=torch.int64, device=dev)
         return z, torch.zeros(0, device=dev), z
     B = Bq.to(torch.int64)
+    if _on_device(soft, q, base):
+        assert soft.stride(1) == 2 and soft.stride(2) == 1 and q.stride(1) == 1
+        cnt, b64, tgt = count.to(torch.int32).contiguous(), base.to(torch.int64).contiguous(), B.contiguous()
+        cut = torch.empty(M - 1, dtype=torch.int64, device=dev)
+        ia, ib, nav = (torch.empty(M - 1, dtype=torch.int32, device=dev) for _ in range(3))
+        _lib_call("lrpt_shard_find_cuts_device", dev, _p(q), q.stride(0) * 4, _p(cnt), _p(b64), M, _p(tgt), _p(cut),
+                  _p(ia), _p(ib), _p(nav))
+        nmin = int(nav.min().item())
+        npairs = nmin if npairs is None else min(npairs, nmin)
+        if npairs < 8:
+            return torch.zeros(M - 1, dtype=torch.int64, device=dev), torch.zeros(M - 1, device=dev), cut
+        k, same = (torch.empty(M - 1, dtype=torch.int32, device=dev) for _ in range(2))
+        _lib_call("lrpt_shard_quadrants_device", dev, _p(soft), soft.stride(0), _p(q), q.stride(0) * 4, _p(b64), M,
+                  _p(ia), _p(ib), npairs, _p(k), _p(same))
+        return k.to(torch.int64), same.to(torch.float32) / npairs, cut
+    if base is not None:
+        q = q.to(torch.int64) + base[:, None]
     a_q, a_s, a_n = q[:-1], soft[:-1], count[:-1]
     b_q, b_s, b_n = q[1:], soft[1:], count[1:]
     ia = _first_at_or_after(a_q, a_n, B)                     # first symbol of row c-1 inside the overlap
@@ -139,12 +182,13 @@ def boundary_quadrants(soft, q, count, Bq, npairs=None):
     return k, same.float().mean(dim=1), cut
 
 
-def stitch(soft, q, count, plan, first_chunk=0, dist=None):
+def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None):
     """Quadrant scan + concatenation of the owned symbols.
 
     soft [M,cap,2] int8, q [M,cap] int64 ABSOLUTE sub-step index (sample*interp + sub-step from the
-    start of the stream), count [M] int64: the chunks this process demodulated, chunk indices
-    first_chunk .. first_chunk+M-1. Single process: pass all chunks. Multi-process (`dist` =
+    start of the stream) -- or row-local with `base` [M] int64 to be added, which is how the GPU engine
+    leaves it (int32; such rows are joined by the library's stitch kernels, csrc/shard_stitch.cu) --
+    count [M] int64: the chunks this process demodulated, chunk indices first_chunk .. first_chunk+M-1. Single process: pass all chunks. Multi-process (`dist` =
     torch.distributed, ranks own consecutive runs of chunks in rank order): the exchange is (a) the
     symbols around the next boundary of a rank's LAST chunk, sent to the next rank, (b) one all-gather
     of an integer per rank -- the prefix sum of quarter turns is then local.
@@ -156,7 +200,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
     M, L, dev = soft.shape[0], plan.interp, soft.device
     big = torch.iinfo(torch.int64).max
     Bq = torch.tensor([plan.cut_target(first_chunk + c) for c in range(1, M)], dtype=torch.int64, device=dev)
-    k, agree, cut = boundary_quadrants(soft, q, count, Bq)
+    k, agree, cut = boundary_quadrants(soft, q, count, Bq, base=base)
 
     k_prev, agree_prev, cut_prev = 0, None, None
     if world > 1:
@@ -167,8 +211,9 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
         if first_chunk + M < plan.nchunks:
             nextB = plan.cut_target(first_chunk + M)
             n = int(count[-1].item())
-            sel = (q[-1, :n] >= nextB - 64 * L).nonzero().squeeze(1)[:width]
-            pack[: sel.numel(), 0] = q[-1, sel]
+            q_last = _abs_row(q, base, M - 1)
+            sel = (q_last[:n] >= nextB - 64 * L).nonzero().squeeze(1)[:width]
+            pack[: sel.numel(), 0] = q_last[sel]
             pack[: sel.numel(), 1:] = soft[-1, sel].to(torch.int64)
             npack[0] = sel.numel()
         recv, nrecv = torch.zeros_like(pack), torch.zeros_like(npack)
@@ -186,7 +231,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
             two_s[0, :n] = recv[:n, 1:].to(torch.int8)
             two_q[0, :n] = recv[:n, 0]
             two_s[1, : soft.shape[1]] = soft[0]
-            two_q[1, : soft.shape[1]] = q[0]
+            two_q[1, : soft.shape[1]] = _abs_row(q, base, 0)
             two_n = torch.stack((torch.tensor(n, dtype=torch.int64, device=dev), count[0]))
             kp, ap, cp = boundary_quadrants(two_s, two_q, two_n,
                                             torch.tensor([plan.cut_target(first_chunk)], device=dev))
@@ -214,15 +259,30 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None):
     if first_chunk + M < plan.nchunks:
         # my last chunk ends where the next rank's first chunk begins: same rule, evaluated locally
         nextB = torch.tensor([plan.cut_target(first_chunk + M)], dtype=torch.int64, device=dev)
-        ia = _first_at_or_after(q[-1:], count[-1:], nextB)
-        pq = torch.gather(q[-1:], 1, (ia - 1).clamp(min=0)[:, None]).squeeze(1)
-        nq = torch.gather(q[-1:], 1, ia.clamp(max=q.shape[1] - 1)[:, None]).squeeze(1)
+        q_last = _abs_row(q, base, M - 1)[None, :]
+        ia = _first_at_or_after(q_last, count[-1:], nextB)
+        pq = torch.gather(q_last, 1, (ia - 1).clamp(min=0)[:, None]).squeeze(1)
+        nq = torch.gather(q_last, 1, ia.clamp(max=q.shape[1] - 1)[:, None]).squeeze(1)
         hi[-1] = torch.where((ia > 0) & (ia < count[-1:]), (pq + nq) // 2, nextB)[0]
     else:
         hi[-1] = plan.nsamples * L - 1                       # nothing from the zero padding
-    cols = torch.arange(soft.shape[1], device=dev)
-    keep = (cols[None, :] < count[:, None]) & (q > lo[:, None]) & (q <= hi[:, None])
-    out = rotate_quarter_turns(soft, K)[keep]
+    if _on_device(soft, q, base):
+        # every row contributes one contiguous run (its sub-step indices ascend): find it, then copy + turn
+        cnt, b64 = count.to(torch.int32).contiguous(), base.to(torch.int64).contiguous()
+        start, ln = (torch.empty(M, dtype=torch.int32, device=dev) for _ in range(2))
+        _lib_call("lrpt_shard_ranges_device", dev, _p(q), q.stride(0) * 4, _p(cnt), _p(b64), M, _p(lo), _p(hi), _p(start), _p(ln))
+        ln64 = ln.to(torch.int64)
+        off = (torch.cumsum(ln64, 0) - ln64).contiguous()
+        total, longest = (int(v) for v in torch.stack((ln64.sum(), ln64.max())).tolist())
+        out = torch.empty((total, 2), dtype=torch.int8, device=dev)
+        turns = K.to(torch.int32).contiguous()
+        _lib_call("lrpt_shard_gather_device", dev, _p(soft), soft.stride(0), M, longest, _p(start), _p(ln), _p(off), _p(turns), _p(out))
+    else:
+        if base is not None:
+            q = q.to(torch.int64) + base[:, None]
+        cols = torch.arange(soft.shape[1], device=dev)
+        keep = (cols[None, :] < count[:, None]) & (q > lo[:, None]) & (q <= hi[:, None])
+        out = rotate_quarter_turns(soft, K)[keep]
     return dict(soft=out, k=k, agreement=agree, boundary_prev=(k_prev, agree_prev),
                 K_first=K_first, K_last=int(K[-1].item()))
 
@@ -267,12 +327,12 @@ class GpuEngine:
         p = self.plan
         base = ((torch.arange(self.first, self.first + self.M, device=self.raw.device, dtype=torch.int64)
                  * p.chunk + offset) * p.interp)
-        return (self.soft.view(self.M, self.cap, 2), self.q.to(torch.int64) + base[:, None],
-                self.nsym.to(torch.int64))
+        # rows stay as the kernel wrote them: int32 sub-step indices counted from the row's own start + a base per row
+        return self.soft.view(self.M, self.cap, 2), self.q, self.nsym.to(torch.int64), base
 
     def run(self, stream=None):
         """Single pass: every local chunk (warm-up + owned + overlap) in one batch launch. Returns
-        soft [M,cap,2] int8, q [M,cap] int64 absolute sub-step indices, count [M] int64 (device)."""
+        soft [M,cap,2] int8, q [M,cap] int32 row-local sub-step indices, count [M] int64, base [M] int64 (device)."""
         n_all = self.plan.n_main + self.plan.overlap
         self.d.reset(stream=stream, asynchronous=True)
         self.d.process_device(self._view(0, n_all), self.soft, nsym=self.nsym, stream=stream, nsamples=n_all)
@@ -311,8 +371,7 @@ class GpuEngine:
         n = p.chunk + p.overlap
         self.d.process_device(self._view(p.warm, n), self.soft, nsym=self.nsym, nsamples=n)
         self.d.sync()
-        soft, q, count = self._result(p.warm)
-        return soft.clone(), q, count.clone()
+        return self._result(p.warm)                          # views of the engine's buffers: valid until pass_c
 
     def pass_c(self):
         """From the imported states: owned + overlap samples starting V samples after the boundary."""
@@ -378,9 +437,10 @@ def run_handoff(eng, plan, first_chunk=0, dist=None):
     if first_chunk == 0 and M < 2 and plan.nchunks > 1:
         raise ValueError("the rank holding chunk 0 needs at least two chunks")
     head = eng.pass_a()
-    soft_b, q_b, n_b = eng.pass_b()
-    scan = stitch(soft_b, q_b, n_b, plan, first_chunk=first_chunk, dist=dist)
+    soft_b, q_b, n_b, base_b = _rows4(eng.pass_b())
+    scan = stitch(soft_b, q_b, n_b, plan, first_chunk=first_chunk, dist=dist, base=base_b)
     K = chunk_turns(scan, M)
+    row0 = soft_b[0, : int(n_b[0].item())].clone() if first_chunk == 0 else None   # pass C reuses the buffers
     turned = eng.rotate_rows(eng.export_rows(), K)
     incoming = turned[:1].clone()                                   # placeholder for the row that has no predecessor
     req = None
@@ -391,30 +451,34 @@ def run_handoff(eng, plan, first_chunk=0, dist=None):
             dist.recv(incoming, rank - 1)
         if req is not None:
             req.wait()
+    if first_chunk == 0 and M == 1:                                 # the whole stream is chunk 0: already exact
+        res = dict(scan)
+        res["soft"] = torch.cat((_as_tensor(head, soft_b.device), row0))
+        res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
+        return res
     eng.import_rows(torch.cat((incoming, turned[:-1])))
-    soft_c, q_c, n_c = eng.pass_c()
+    soft_c, q_c, n_c, base_c = _rows4(eng.pass_c())
     shifted = dataclasses.replace(plan, cut_shift=plan.overlap)
     if first_chunk == 0:
-        if M == 1:                                                  # the whole stream is chunk 0: already exact
-            res = dict(scan)
-            res["soft"] = torch.cat((_as_tensor(head, soft_b.device), soft_b[0, : int(n_b[0].item())]))
-            res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
-            return res
-        # rows 0 and 1 are one exact trajectory: row 0's pass-B symbols, then row 1's pass-C symbols
-        n0, n1 = int(n_b[0].item()), int(n_c[1].item())
-        cap = max(soft_c.shape[1], n0 + n1)
-        soft = torch.zeros((M - 1, cap, 2), dtype=torch.int8, device=soft_c.device)
-        q = torch.zeros((M - 1, cap), dtype=torch.int64, device=soft_c.device)
-        soft[0, :n0], q[0, :n0] = soft_b[0, :n0], q_b[0, :n0]
-        soft[0, n0: n0 + n1], q[0, n0: n0 + n1] = soft_c[1, :n1], q_c[1, :n1]
-        soft[1:, : soft_c.shape[1]], q[1:, : soft_c.shape[1]] = soft_c[2:], q_c[2:]
-        count = torch.cat((torch.tensor([n0 + n1], dtype=torch.int64, device=soft_c.device), n_c[2:]))
-        res = stitch(soft, q, count, shifted, first_chunk=1, dist=dist)
-        res["soft"] = torch.cat((_as_tensor(head, soft.device), res["soft"]))
+        # rows 0 and 1 are one exact trajectory: the head, row 0's pass-B symbols, then row 1's pass-C symbols up
+        # to its cut with row 2 -- i.e. the final table is rows 1.. with nothing cut off the front of row 1
+        res = stitch(soft_c[1:], q_c[1:], n_c[1:], shifted, first_chunk=1, dist=dist,
+                     base=None if base_c is None else base_c[1:])
+        res["soft"] = torch.cat((_as_tensor(head, soft_c.device), row0, res["soft"]))
     else:
-        res = stitch(soft_c, q_c, n_c, shifted, first_chunk=first_chunk, dist=dist)
+        res = stitch(soft_c, q_c, n_c, shifted, first_chunk=first_chunk, dist=dist, base=base_c)
     res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
     return res
+
+
+def _rows4(rows):
+    """(soft, q, count[, base]) as an engine returns it -> always four items."""
+    return tuple(rows) if len(rows) == 4 else tuple(rows) + (None,)
+
+
+def _stitch_rows(rows, plan, **kw):
+    soft, q, count, base = _rows4(rows)
+    return stitch(soft, q, count, plan, base=base, **kw)
 
 
 def _as_tensor(x, device):
@@ -444,12 +508,12 @@ class ShardedDemod:
         if self.handoff:
             res = run_handoff(eng, plan, first_chunk=c0, dist=self.dist)
         elif not self.two_pass:
-            res = stitch(*eng.run(), plan, first_chunk=c0, dist=self.dist)
+            res = _stitch_rows(eng.run(), plan, first_chunk=c0, dist=self.dist)
         else:
             head = eng.warm_up()
-            scan = stitch(*eng.owned(), plan, first_chunk=c0, dist=self.dist)
+            scan = _stitch_rows(eng.owned(), plan, first_chunk=c0, dist=self.dist)
             K = chunk_turns(scan, M)
-            res = stitch(*eng.owned(K), plan, first_chunk=c0, dist=self.dist)
+            res = _stitch_rows(eng.owned(K), plan, first_chunk=c0, dist=self.dist)
             res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
             if c0 == 0:
                 res["soft"] = torch.cat((head, res["soft"]))

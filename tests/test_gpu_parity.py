@@ -274,6 +274,33 @@ def test_lane_kernel_many_warps_per_sm(name, oracle_mod, lib):
         assert_state_equal(d.state(s), o)
 
 
+@pytest.mark.parametrize("wf", ["0", "1"])
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_lane_window_formats(name, wf, oracle_mod, lib, monkeypatch):
+    """The lane kernel's delay-line window in the input's own type (LRPT_LANE_WF=0) and as float pairs
+    (=1; what the launch picks by itself when it costs no warp): both bit-exact, ragged launches, 70 streams
+    (3 warps, idle lanes in the last), float symbols and state included."""
+    monkeypatch.setenv("LRPT_LANE_WF", wf)
+    cfg = CONFIGS[name]
+    n = 40_000
+    raw = np.stack([make_case(name, n, seed=400 + s, cfo_hz=-600.0 + 17 * s) for s in range(7)])
+    raw = np.concatenate([raw] * 10)
+    d = demod_for(cfg, "lane", nstreams=70)
+    parts, total = [], np.zeros(70, np.int64)
+    for a, b in ((0, 17), (17, 18), (18, 30_001), (30_001, n)):
+        soft, counts, symf = d.process_batch(np.ascontiguousarray(raw[:, 2 * a: 2 * b]), want_float=True)
+        parts.append((soft, counts.astype(np.int64), symf))
+    for s in (0, 3, 31, 32, 63, 64, 69):
+        o = oracle_mod.Oracle(**cfg)
+        w = o.process(raw[s])
+        got = np.concatenate([p[0][s, :p[1][s]] for p in parts])
+        gotf = np.concatenate([p[2][s, :p[1][s]] for p in parts])
+        assert got.shape[0] == w.nsym, s
+        assert np.array_equal(got, w.soft), s
+        assert np.array_equal(bits(gotf), bits(w.sym)), s
+        assert_state_equal(d.state(s), o)
+
+
 def test_full_size_batch_twins_and_samples(oracle_mod, lib):
     """BASELINE-size batch (75776 streams = 16 warps on every SM): a size-independent property --
     streams with identical input give identical output, checked over the WHOLE batch -- plus sampled

@@ -225,7 +225,10 @@ def _rank_main(rank, world, port, out_dir):
     plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
     c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
     soft, q, count = oracle_chunks(raw, plan, c0, c1)
-    res = sharded.stitch(soft, q, count, plan, first_chunk=c0, dist=dist)
+    # rows as the GPU engine hands them over: int32 indices counted from the row's own start + a base per row
+    base = torch.tensor([plan.start(c) * plan.interp for c in range(c0, c1)], dtype=torch.int64)
+    q_local = torch.where(q > 0, q - base[:, None], q).to(torch.int32)
+    res = sharded.stitch(soft, q_local, count, plan, first_chunk=c0, dist=dist, base=base)
     np.save(os.path.join(out_dir, "part%d.npy" % rank), res["soft"].numpy())
     np.save(os.path.join(out_dir, "meta%d.npy" % rank),
             np.array([res["K_first"], res["K_last"], res["boundary_prev"][0] or 0], np.int64))
@@ -273,6 +276,7 @@ def test_gpu_sharded_equals_oracle_sharded(single, stream, lib):
                                 rrc_order=32, interp_factor=5, two_pass=False)
     assert out["plan"].nchunks == plan.nchunks and out["launches"] == 1
     assert torch.equal(out["k"].cpu(), res["k"])
+    assert torch.allclose(out["agreement"].cpu(), res["agreement"], atol=1e-6)
     assert np.array_equal(out["soft"].cpu().numpy(), res["soft"].numpy())
 
 
