@@ -475,8 +475,12 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
         a.warm = 150000 if a.handoff else 400000
     plan = sharded.Plan(N, a.chunk, a.warm, 8192, interp)
     period = synth.baseband(FS, symrate=symrate, oqpsk=bool(oqpsk), periodic=True, seed=3).astype(np.complex64)
-    raw = synth.device_long_stream(period, N, total=plan.padded, bps=bps, sps=FS / symrate)
-    kw = dict(chunk=a.chunk, warm=a.warm, overlap=8192, device=local, dist=dist if world > 1 else None,
+    # every rank holds only its time slice of the stream (+ the warm-up and overlap its chunks over-read)
+    c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
+    s0 = plan.start(c0)
+    span = plan.start(c1 - 1) + plan.n_main + 2 * plan.overlap - s0
+    raw = synth.device_long_stream(period, N, total=span, bps=bps, sps=FS / symrate, first=s0)
+    kw = dict(chunk=a.chunk, warm=a.warm, overlap=8192, device=local, dist=dist if world > 1 else None, raw_first=s0,
               symrate=symrate, bps=bps, rrc_order=order, interp_factor=interp, two_pass=not a.single_pass,
               handoff=a.handoff)
 
@@ -511,7 +515,7 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
     if rank == 0:
         # Tier-S epsilon on this rank's head of the stream against the sequential CPU oracle
         from oracle import pyoracle
-        ncheck = min(N, plan.boundary(min(plan.nchunks - 1, 40)))
+        ncheck = min(N, span, plan.boundary(min(plan.nchunks - 1, 40)))
         o = pyoracle.Oracle(symrate=symrate, oqpsk=oqpsk, bps=bps, order=order, interp=interp)
         w = o.process(raw[: 2 * ncheck].cpu().numpy(), want_float=False)
         got = res["soft"][: w.nsym].cpu().numpy()
@@ -525,7 +529,7 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
                 "config": {"workload": "%s; ONE stream of %d samples time-sharded: %d chunks of %d, warm-up %d, overlap 8192, %s"
                            % (label, N, plan.nchunks, a.chunk, a.warm, "state hand-off between chunks" if a.handoff else "single pass" if a.single_pass else "two-pass lock-point alignment"),
                            "parity": "Tier-S (statistical): chunk 0 bit-exact, later chunks see tier_s",
-                           "l2": "stream (%.1f GB) larger than L2" % (N * (bps // 4) / 1e9)},
+                           "l2": "stream (%.1f GB, %.1f GB resident per rank) larger than L2" % (N * (bps // 4) / 1e9, span * (bps // 4) / 1e9)},
                 "gpu_launches": int(launches), "symbols_per_step": int(nsym.item()),
                 "min_boundary_agreement": float(agree.item()), "tier_s": eps, "clocks": clk.summary()}
         if cpu_base is not None:

@@ -305,9 +305,12 @@ def chunk_turns(res, M):
 class GpuEngine:
     """Chunks of one device-resident raw stream through liblrpt_b200.so, one recurrence lane each."""
 
-    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, **cfg):
+    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, raw_first=0, **cfg):
+        """raw: device tensor of the raw dtype whose item 0 is I of stream sample `raw_first` -- the whole
+        (padded) stream, or just the span this engine's chunks read: [plan.start(first_chunk),
+        plan.start(last chunk) + n_main + 2*overlap)."""
         from .demod import Demod
-        self.plan, self.raw, self.first = plan, raw, first_chunk
+        self.plan, self.raw, self.first, self.raw_first = plan, raw, first_chunk, raw_first
         self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
         self.d = Demod(nstreams=self.M, device=device, interp_factor=plan.interp, **cfg)
         n_all = plan.n_main + plan.overlap
@@ -321,7 +324,7 @@ class GpuEngine:
     def _view(self, first_sample_of_chunk0, nsamples):
         p = self.plan
         return torch.as_strided(self.raw, (self.M, 2 * nsamples), (2 * p.chunk, 1),
-                                storage_offset=2 * (p.start(self.first) + first_sample_of_chunk0))
+                                storage_offset=2 * (p.start(self.first) + first_sample_of_chunk0 - self.raw_first))
 
     def _result(self, offset):
         p = self.plan
@@ -490,7 +493,7 @@ class ShardedDemod:
     are built once; run() can be called repeatedly, e.g. by bench.py)."""
 
     def __init__(self, raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
-                 interp_factor=5, two_pass=True, handoff=False, **cfg):
+                 interp_factor=5, two_pass=True, handoff=False, raw_first=0, **cfg):
         if cfg.get("oqpsk"):
             raise NotImplementedError("time-sharding resolves the k*90 degree ambiguity of QPSK only")
         self.plan = plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
@@ -500,7 +503,11 @@ class ShardedDemod:
         if plan.nchunks < world:
             raise ValueError("fewer chunks (%d) than ranks (%d)" % (plan.nchunks, world))
         self.c0, self.c1 = split_chunks(plan.nchunks, world, rank)
-        self.eng = GpuEngine(raw, plan, device=device, first_chunk=self.c0, nchunks=self.c1 - self.c0, **cfg)
+        need = (plan.start(self.c1 - 1) + plan.n_main + 2 * plan.overlap - raw_first) * 2
+        if raw_first > plan.start(self.c0) or raw.numel() < need:
+            raise ValueError("raw must hold samples [%d, %d) for chunks %d..%d" % (plan.start(self.c0), raw_first + need // 2, self.c0, self.c1 - 1))
+        self.eng = GpuEngine(raw, plan, device=device, first_chunk=self.c0, nchunks=self.c1 - self.c0,
+                             raw_first=raw_first, **cfg)
 
     def run(self):
         eng, plan, c0, M = self.eng, self.plan, self.c0, self.c1 - self.c0
@@ -526,9 +533,10 @@ class ShardedDemod:
 
 def demod_sharded(raw, nsamples, **kw):
     """One long stream, time-sharded over this process's GPU and, with dist=torch.distributed
-    (initialised), over ranks: rank r takes a consecutive run of chunks and reads them from ITS copy of
-    the stream (over-reading warm-up and overlap instead of communicating samples). raw: 1-D device
-    tensor of the raw dtype with at least 2*Plan.padded items (zeros after 2*nsamples).
+    (initialised), over ranks: rank r takes a consecutive run of chunks (split_chunks) and needs only the
+    samples those read -- its time slice plus warm-up and overlap, which it over-reads instead of
+    communicating samples. raw: 1-D device tensor of the raw dtype starting at stream sample `raw_first`
+    (default 0: the whole stream, at least 2*Plan.padded items, zeros after 2*nsamples).
 
     two_pass=False: one launch; chunks keep whatever lock point they acquired and are de-rotated after
     the fact. Chunks that locked an odd number of quarter turns away see the OTHER bit stream on the Q

@@ -176,35 +176,41 @@ def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 7
 
 
 def device_long_stream(period, nsamples, total=None, bps=16, fs=230000, sps=230000 / 72000, seed=11, cfo_hz=700.0,
-                       phase=0.7, esn0_db=12.0, rms=6000.0, device="cuda", block=1 << 25):
+                       phase=0.7, esn0_db=12.0, rms=6000.0, device="cuda", block=1 << 25, first=0):
     """ONE long raw stream on the device (time-sharding workload): the tileable period repeated, a carrier
     offset (rounded to a multiple of fs/len(period)), noise, quantisation. Returns a 1-D tensor with
-    2*total items (total >= nsamples; the tail beyond nsamples is zero padding)."""
+    2*total items holding samples [first, first + total) of the stream (default: all of it, total >=
+    nsamples); samples at or beyond nsamples are zero padding. The noise is seeded per `block` of absolute
+    sample indices, so any window of the stream comes out the same whichever rank generates it."""
     import torch
 
     dt = {8: torch.uint8, 16: torch.int16, 32: torch.float32}[bps]
-    total = nsamples if total is None else total
+    total = nsamples - first if total is None else total
     P = int(period.size)
     base = torch.from_numpy(np.ascontiguousarray(period.astype(np.complex64))).to(device)
     out = torch.zeros(2 * total, dtype=dt, device=device)
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
     step = fs / P
     cfo = step * round(cfo_hz / step)
     sigma = float(np.sqrt(sps / (10 ** (esn0_db / 10)) / 2)) if esn0_db is not None else 0.0
     dc = torch.tensor([30.0, -20.0], device=device)
-    for n0 in range(0, nsamples, block):
-        n1 = min(nsamples, n0 + block)
+    end = min(nsamples, first + total)
+    for b in range(first // block, (max(end, first + 1) - 1) // block + 1):
+        n0, n1 = max(first, b * block), min(end, (b + 1) * block)
+        if n1 <= n0:
+            continue
         n = torch.arange(n0, n1, device=device)
         arg = torch.remainder(2 * np.pi / fs * cfo * n.to(torch.float64) + phase, 2 * np.pi).to(torch.float32)
         y = base[n % P] * torch.polar(torch.ones_like(arg), arg)
         if sigma:
-            y = y + sigma * torch.complex(torch.randn(y.shape, device=device, generator=g),
-                                          torch.randn(y.shape, device=device, generator=g))
+            g.manual_seed(seed * 1000003 + b)                # the whole block's noise, then this window's part of it
+            nz = torch.complex(torch.randn(block, device=device, generator=g), torch.randn(block, device=device, generator=g))
+            y = y + sigma * nz[n0 - b * block: n1 - b * block]
+            del nz
         v = torch.view_as_real(y)
         if bps == 8:
             v = ((v * (64.0 / 3.0)).round() + 128).clamp(0, 255)
         else:
             v = ((v * rms) + dc).round().clamp(-32768, 32767)
-        out[2 * n0: 2 * n1] = v.reshape(-1).to(dt)
+        out[2 * (n0 - first): 2 * (n1 - first)] = v.reshape(-1).to(dt)
     return out

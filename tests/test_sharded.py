@@ -391,3 +391,16 @@ def test_gpu_handoff_equals_oracle_handoff(stream, lib):
                                 rrc_order=32, interp_factor=5, handoff=True)
     assert torch.equal(out["first_pass"]["K"].cpu(), want["first_pass"]["K"])
     assert np.array_equal(out["soft"].cpu().numpy(), want["soft"].numpy())
+
+
+def test_long_stream_windows_are_consistent():
+    """Every rank generates only its time slice of the synthetic stream (bench.py --mode sharded): a window
+    must hold exactly the samples the whole stream holds there, zero padding beyond the end included."""
+    from meteor_demod_b200 import synth
+    per = synth.baseband(23000, periodic=True, seed=3).astype(np.complex64)
+    n = 20_000
+    full = synth.device_long_stream(per, n, total=n + 3000, device="cpu", block=4096)
+    assert full.numel() == 2 * (n + 3000) and not full[2 * n:].any() and full[: 2 * n].any()
+    for first, total in ((0, 5000), (4096, 4096), (5000, 9000), (12_345, 10_655), (19_999, 50), (20_000, 10)):
+        win = synth.device_long_stream(per, n, total=total, device="cpu", block=4096, first=first)
+        assert torch.equal(win, full[2 * first: 2 * (first + total)]), (first, total)
