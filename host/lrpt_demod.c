@@ -18,6 +18,9 @@
  * (one lrpt_process call per input slab instead), and the final-flush length bug
  * (main.c:321 writes 2*ring_idx bytes, the second half stale or out of bounds) unless
  * --ref-compatible-tail asks for the reference's byte count.
+ * Beyond the reference: several input files on one command line are demodulated TOGETHER as the
+ * streams of one batch (lrpt_process_batch; archive reprocessing) -- every file's output is what a
+ * separate run on it writes, into <input>.s.
  */
 #include <getopt.h>
 #include <math.h>
@@ -55,7 +58,7 @@ static struct option longopts[] = {
 static void
 usage(const char *pname)
 {
-	fprintf(stderr, "Usage: %s [options] file_in\n", pname);
+	fprintf(stderr, "Usage: %s [options] file_in [file_in2 ...]\n", pname);
 	fprintf(stderr,
 	        "   -B, --batch             Script-friendly status output (no control characters)\n"
 	        "   -m, --mode <mode>       Modulation scheme (default: qpsk, valid modes: qpsk, oqpsk)\n"
@@ -68,6 +71,7 @@ usage(const char *pname)
 	        "       --stdout            Write output symbols to stdout (implies -B, -q)\n"
 	        "       --device <n>        CUDA device ordinal (default: 0)\n"
 	        "       --ref-compatible-tail  Final flush writes the reference's byte count (main.c:321)\n"
+	        "   Several input files are demodulated together as one batch; output goes to <file_in>.s each\n"
 	        "\n"
 	        "   -h, --help              Print this help screen\n"
 	        "   -v, --version           Print version info\n"
@@ -131,6 +135,140 @@ now_ms(void)
 	return ts.tv_sec*1e3 + ts.tv_nsec*1e-6;
 }
 
+/* Soft symbols leave in 512-symbol blocks, a block only if the PLL had locked once when it completed;
+ * the last partial block always (main.c:305-323). One of these per output file. */
+struct egress {
+	FILE *out;
+	int8_t ring[2*RINGSIZE];                               /* the partial block carried between calls */
+	int8_t prev_block[2*RINGSIZE];                         /* last complete block, for --ref-compatible-tail */
+	size_t ring_idx;                                       /* int8 values in `ring`, as in main.c:291 */
+	unsigned long long nsym_total, bytes_out;
+};
+
+static void
+egress_push(struct egress *e, const int8_t *soft, size_t nsym, long long first_lock)
+{
+	size_t i = 0;
+	while (i < 2*nsym) {
+		size_t take = 2*RINGSIZE - e->ring_idx;
+		if (take > 2*nsym - i) take = 2*nsym - i;
+		memcpy(e->ring + e->ring_idx, soft + i, take);
+		e->ring_idx += take; i += take;
+		if (e->ring_idx == 2*RINGSIZE) {
+			const unsigned long long block_last = e->nsym_total + i/2 - 1;      /* index of the block's last symbol */
+			if (first_lock >= 0 && (unsigned long long)first_lock <= block_last) {
+				fwrite(e->ring, RINGSIZE, 2, e->out);
+				e->bytes_out += 2*RINGSIZE;
+			}
+			memcpy(e->prev_block, e->ring, sizeof(e->ring));
+			e->ring_idx = 0;
+		}
+	}
+	e->nsym_total += nsym;
+}
+
+static void
+egress_finish(struct egress *e, int ref_tail)
+{
+	/* final flush: not lock-gated (main.c:321) */
+	fwrite(e->ring, 1, e->ring_idx, e->out);
+	e->bytes_out += e->ring_idx;
+	if (ref_tail && e->ring_idx) {
+		/* the reference writes ring_idx more bytes: stale ring content, then (beyond the ring) out of bounds */
+		size_t k;
+		for (k = e->ring_idx; k < 2*e->ring_idx; k++) fputc(k < 2*RINGSIZE ? e->prev_block[k] : 0, e->out);
+	}
+}
+
+/* whole 32 KiB blocks only: a trailing partial block is never consumed (wavfile.c:55). Returns bytes usable. */
+static size_t
+read_blocks(FILE *in, uint8_t *dst, size_t want, int *eof)
+{
+	size_t got = 0;
+	while (got < want) {
+		size_t r = fread(dst + got, 1, want - got, in);
+		if (!r) break;
+		got += r;
+	}
+	*eof = got < want;
+	return got/FILE_BLOCK*FILE_BLOCK;
+}
+
+/* Several recordings as the streams of one batch. All share the command line's settings and must agree
+ * on sample rate and sample format; lengths may differ (a finished stream idles on silence, its output
+ * is no longer written). Output of <input> goes to <input>.s. */
+static int
+run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps_opt, float symrate, int quiet, int ref_tail)
+{
+	struct input { FILE *in; int eof; size_t avail; struct egress eg; lrpt_status_t last; } *f = calloc((size_t)nfiles, sizeof(*f));
+	int samplerate = -1, bps = 0, i, rc, active = nfiles;
+	char path[4096];
+	if (!f) { fprintf(stderr, "out of memory\n"); return 1; }
+	for (i = 0; i < nfiles; i++) {
+		int sr = samplerate_opt, b = bps_opt;
+		if (!(f[i].in = fopen(names[i], "rb"))) { fprintf(stderr, "Could not open input file\n"); return 1; }
+		if (wav_parse(f[i].in, &sr, &b)) fseek(f[i].in, 0, SEEK_SET);
+		if (sr < 0) { fprintf(stderr, "Could not auto-detect sample rate. Please specify it with -s <samplerate>\n"); return 1; }
+		if (!b) { fprintf(stderr, "Could not auto-detect bits per sample, assuming 16\n"); b = 16; }
+		if (i && (sr != samplerate || b != bps)) {
+			fprintf(stderr, "%s: %d Hz / %d bits differs from %s (%d Hz / %d bits); one batch needs one format\n",
+			        names[i], sr, b, names[0], samplerate, bps);
+			return 1;
+		}
+		samplerate = sr; bps = b;
+		snprintf(path, sizeof(path), "%s.s", names[i]);
+		if (!(f[i].eg.out = fopen(path, "wb"))) { fprintf(stderr, "Could not open output file\n"); return 1; }
+	}
+	if (bps != 8 && bps != 16 && bps != 32) { fprintf(stderr, "Unsupported bits per sample: %d\n", bps); return 1; }
+	p.samplerate = samplerate; p.bps = bps; p.nstreams = nfiles;
+	lrpt_demod_t *h = NULL;
+	if ((rc = lrpt_create(&h, &p))) { fprintf(stderr, "lrpt_create failed: %s\n", lrpt_strerror(rc)); return 1; }
+
+	const size_t bytes_per_sample = (size_t)bps/4;
+	size_t slab_bytes = (size_t)SLAB_BLOCKS*FILE_BLOCK;
+	while (slab_bytes > FILE_BLOCK && slab_bytes*(size_t)nfiles > ((size_t)1 << 31)) slab_bytes /= 2;   /* <= 2 GiB of input per call */
+	const size_t cap = slab_bytes/bytes_per_sample;
+	uint8_t *raw = calloc((size_t)nfiles, slab_bytes);
+	int8_t *soft = malloc((size_t)nfiles*2*cap);
+	uint32_t *nsym = calloc((size_t)nfiles, sizeof(*nsym));
+	if (!raw || !soft || !nsym) { fprintf(stderr, "out of memory\n"); return 1; }
+
+	while (active) {
+		/* refill: every stream still open reads up to one slab; the call covers what ALL of them have */
+		size_t common = slab_bytes;
+		for (i = 0; i < nfiles; i++) {
+			if (!f[i].in) continue;
+			if (!f[i].avail && !f[i].eof) f[i].avail = read_blocks(f[i].in, raw + (size_t)i*slab_bytes, slab_bytes, &f[i].eof);
+			if (!f[i].avail) {                                  /* finished: final flush, then silence */
+				egress_finish(&f[i].eg, ref_tail);
+				fclose(f[i].eg.out); fclose(f[i].in); f[i].in = NULL; active--;
+				memset(raw + (size_t)i*slab_bytes, bps == 8 ? 128 : 0, slab_bytes);
+				continue;
+			}
+			if (f[i].avail < common) common = f[i].avail;
+		}
+		if (!active) break;
+		rc = lrpt_process_batch(h, raw, slab_bytes, common/bytes_per_sample, soft, 2*cap, cap, nsym, NULL, 0);
+		if (rc) { fprintf(stderr, "lrpt_process_batch failed: %s (%s)\n", lrpt_strerror(rc), lrpt_last_error(h)); return 1; }
+		for (i = 0; i < nfiles; i++) {
+			if (!f[i].in) continue;
+			lrpt_status(h, i, &f[i].last);                      /* the stream's state while it still has input */
+			egress_push(&f[i].eg, soft + (size_t)i*2*cap, nsym[i], f[i].last.first_lock_symbol);
+			f[i].avail -= common;                               /* keep the unconsumed rest at the front of the row */
+			if (f[i].avail) memmove(raw + (size_t)i*slab_bytes, raw + (size_t)i*slab_bytes + common, f[i].avail);
+		}
+	}
+	if (!quiet) {
+		for (i = 0; i < nfiles; i++)
+			printf("%s -> %s.s: %llu symbols, %llu bytes, Carrier: %+7.1f Hz, Locked: %s\n", names[i], names[i],
+			       f[i].eg.nsym_total, f[i].eg.bytes_out, f[i].last.pll_freq*symrate/(2*M_PI)*(p.oqpsk ? 2 : 1),
+			       f[i].last.locked ? "Yes" : "No");
+	}
+	lrpt_destroy(h);
+	free(raw); free(soft); free(nsym); free(f);
+	return 0;
+}
+
 int
 main(int argc, char *argv[])
 {
@@ -168,6 +306,16 @@ main(int argc, char *argv[])
 	if (!output_fname) output_fname = gen_fname();
 	if (update_interval < 0) update_interval = batch ? 2000 : 50;
 	if (stdout_mode) { batch = 1; quiet = 1; }
+
+	if (argc - optind > 1) {                                 /* several recordings: one batch, <input>.s each */
+		lrpt_params_t bp;
+		if (stdout_mode) { fprintf(stderr, "--stdout needs a single input\n"); return 1; }
+		memset(&bp, 0, sizeof(bp));
+		bp.pll_bw = pll_bw; bp.sym_bw = 0.00005f; bp.freq_max = freq_max_delta;
+		bp.symrate = (int)symrate; bp.interp_factor = interp_factor; bp.rrc_order = rrc_order; bp.oqpsk = oqpsk;
+		bp.device = device; bp.kernel = LRPT_KERNEL_AUTO;
+		return run_batch(argc - optind, argv + optind, bp, samplerate, bps, symrate, quiet, ref_tail);
+	}
 
 	if (!strcmp(argv[optind], "-")) { in = stdin; batch = 1; }
 	else if (!(in = fopen(argv[optind], "rb"))) { fprintf(stderr, "Could not open input file\n"); return 1; }
@@ -207,48 +355,23 @@ main(int argc, char *argv[])
 	const size_t cap = slab_samples;                       /* a symbol needs at least one sample in any sane setup */
 	uint8_t *raw = malloc(slab_bytes);
 	int8_t *soft = malloc(2*cap);
-	int8_t ring[2*RINGSIZE];                               /* the partial block carried between slabs */
-	int8_t prev_block[2*RINGSIZE];                         /* last complete block, for --ref-compatible-tail */
-	size_t ring_idx = 0;                                   /* int8 values in `ring`, as in main.c:291 */
-	unsigned long long nsym_total = 0, bytes_out = 0, bytes_in = 0;
+	struct egress eg;
+	unsigned long long bytes_in = 0;
 	long long first_lock = -1;
 	double last_status = now_ms();
-	memset(prev_block, 0, sizeof(prev_block));
+	memset(&eg, 0, sizeof(eg));
+	eg.out = out;
 	if (!raw || !soft) { fprintf(stderr, "out of memory\n"); return 1; }
 
 	for (;;) {
-		/* whole 32 KiB blocks only: a trailing partial block is never consumed (wavfile.c:55) */
-		size_t got = 0;
-		while (got < slab_bytes) {
-			size_t r = fread(raw + got, 1, slab_bytes - got, in);
-			if (!r) break;
-			got += r;
-		}
-		const size_t use = got/FILE_BLOCK*FILE_BLOCK;
+		int eof;
+		const size_t use = read_blocks(in, raw, slab_bytes, &eof);
 		if (!use) break;
 		size_t nsym = 0;
 		rc = lrpt_process(h, raw, use/bytes_per_sample, soft, cap, &nsym, &first_lock);
 		if (rc) { fprintf(stderr, "lrpt_process failed: %s (%s)\n", lrpt_strerror(rc), lrpt_last_error(h)); return 1; }
 		bytes_in += use;
-
-		/* 512-symbol blocks, written iff the PLL had locked once when the block completed (main.c:308-316) */
-		size_t i = 0;
-		while (i < 2*nsym) {
-			size_t take = 2*RINGSIZE - ring_idx;
-			if (take > 2*nsym - i) take = 2*nsym - i;
-			memcpy(ring + ring_idx, soft + i, take);
-			ring_idx += take; i += take;
-			if (ring_idx == 2*RINGSIZE) {
-				const unsigned long long block_last = nsym_total + i/2 - 1;      /* index of the block's last symbol */
-				if (first_lock >= 0 && (unsigned long long)first_lock <= block_last) {
-					fwrite(ring, RINGSIZE, 2, out);
-					bytes_out += 2*RINGSIZE;
-				}
-				memcpy(prev_block, ring, sizeof(ring));
-				ring_idx = 0;
-			}
-		}
-		nsym_total += nsym;
+		egress_push(&eg, soft, nsym, first_lock);
 
 		if (!quiet && now_ms() - last_status >= update_interval) {
 			lrpt_status_t st;
@@ -261,17 +384,10 @@ main(int argc, char *argv[])
 			fflush(stdout);
 			last_status = now_ms();
 		}
-		if (got < slab_bytes) break;                          /* EOF */
+		if (eof) break;
 	}
 
-	/* final flush: not lock-gated (main.c:321) */
-	fwrite(ring, 1, ring_idx, out);
-	bytes_out += ring_idx;
-	if (ref_tail && ring_idx) {
-		/* the reference writes ring_idx more bytes: stale ring content, then (beyond the ring) out of bounds */
-		size_t k;
-		for (k = ring_idx; k < 2*ring_idx; k++) fputc(k < 2*RINGSIZE ? prev_block[k] : 0, out);
-	}
+	egress_finish(&eg, ref_tail);
 	if (!quiet) {
 		lrpt_status_t st;
 		lrpt_status(h, 0, &st);

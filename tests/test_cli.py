@@ -102,3 +102,32 @@ def test_usage_and_errors(host, tmp_path):
     raw.write_bytes(b"\0" * 70000)
     r = subprocess.run([host, "-B", "-q", "-o", str(tmp_path / "o"), str(raw)], capture_output=True)
     assert r.returncode == 1 and b"Could not auto-detect sample rate" in r.stderr
+
+
+def test_several_recordings_as_one_batch(host, oracle_mod, tmp_path):
+    """Beyond the reference's command line: several inputs on one command line run as the streams of ONE batch
+    (lrpt_process_batch). Every output file must be byte-identical to what a separate run writes -- the egress
+    rules per file (whole 32 KiB blocks, lock gating, final flush) and different lengths included."""
+    from meteor_demod_b200 import synth
+    lens = (700_123, 65_536, 401_000, 0, 1_300_000)
+    wavs, raws = [], []
+    for i, n in enumerate(lens):
+        raw = synth.make_raw(max(n, 1), cfo_hz=-120.0 + 90 * i, seed=40 + i)[: 2 * n]
+        w = tmp_path / ("pass%d.wav" % i)
+        w.write_bytes(synth.wav_header(raw.nbytes) + raw.tobytes())
+        wavs.append(w)
+        raws.append(raw)
+    r = run([host, "-B"] + [str(w) for w in wavs])
+    assert r.stdout.count(b"symbols") == len(lens)
+    for w, raw in zip(wavs, raws):
+        want, nsym = expected(raw.tobytes(), 16, oracle_mod, False)
+        got = (tmp_path / (w.name + ".s")).read_bytes()
+        assert got == want, w.name
+    single = tmp_path / "single.s"
+    run([host, "-B", "-q", "-o", str(single), str(wavs[4])])
+    assert single.read_bytes() == (tmp_path / "pass4.wav.s").read_bytes()
+    # one batch needs one sample format
+    odd = tmp_path / "odd.wav"
+    odd.write_bytes(synth.wav_header(8, bps=8) + b"\x80" * 8)
+    r = subprocess.run([host, "-B", "-q", str(wavs[0]), str(odd)], capture_output=True)
+    assert r.returncode == 1 and b"one batch needs one format" in r.stderr
