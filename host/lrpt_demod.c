@@ -40,7 +40,7 @@
 #define VERSION "1.0-b200"
 #endif
 
-enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL };
+enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD };
 
 static struct option longopts[] = {
 	{ "batch",        0, NULL, 'B' }, { "pll-bw",       1, NULL, 'b' },
@@ -51,7 +51,7 @@ static struct option longopts[] = {
 	{ "symrate",      1, NULL, 'r' }, { "stdout",       0, NULL, OPT_STDOUT },
 	{ "samplerate",   1, NULL, 's' }, { "bps",          1, NULL, 'S' },
 	{ "version",      0, NULL, 'v' }, { "device",       1, NULL, OPT_DEVICE },
-	{ "ref-compatible-tail", 0, NULL, OPT_REFTAIL },
+	{ "ref-compatible-tail", 0, NULL, OPT_REFTAIL }, { "shard", 1, NULL, OPT_SHARD },
 	{ NULL, 0, NULL, 0 }
 };
 
@@ -71,6 +71,9 @@ usage(const char *pname)
 	        "       --stdout            Write output symbols to stdout (implies -B, -q)\n"
 	        "       --device <n>        CUDA device ordinal (default: 0)\n"
 	        "       --ref-compatible-tail  Final flush writes the reference's byte count (main.c:321)\n"
+	        "       --shard <samples>   Offline speed-up for ONE long recording: cut it into chunks of <samples>\n"
+	        "                           (e.g. 256k) demodulated side by side on the GPU and joined; QPSK only;\n"
+	        "                           statistical parity (the first two chunks are exact), see DESIGN.md\n"
 	        "   Several input files are demodulated together as one batch; output goes to <file_in>.s each\n"
 	        "\n"
 	        "   -h, --help              Print this help screen\n"
@@ -269,12 +272,52 @@ run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps
 	return 0;
 }
 
+/* --shard: the whole recording (whole 32 KiB blocks of it, wavfile.c:55) in memory, one lrpt_sharded_process
+ * call, then the reference's egress rules (main.c:305-323) on the joined symbols. */
+static int
+run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float symrate, int quiet, int ref_tail)
+{
+	size_t have = 0, room = (size_t)64 << 20;
+	uint8_t *raw = malloc(room);
+	int eof = 0;
+	while (raw && !eof) {
+		if (room - have < (size_t)FILE_BLOCK*SLAB_BLOCKS) {
+			uint8_t *grown = realloc(raw, room *= 2);
+			if (!grown) { free(raw); raw = NULL; break; }
+			raw = grown;
+		}
+		have += read_blocks(in, raw + have, (size_t)FILE_BLOCK*SLAB_BLOCKS, &eof);
+	}
+	if (!raw) { fprintf(stderr, "out of memory\n"); return 1; }
+	const size_t nsamples = have/((size_t)p->bps/4);
+	const size_t cap = (size_t)((double)nsamples*p->symrate/p->samplerate*1.02) + 64;
+	int8_t *soft = malloc(2*cap);
+	if (!soft) { fprintf(stderr, "out of memory\n"); return 1; }
+	lrpt_shard_plan_t plan = { (chunk + 7)/8*8, 150000, 8192 };
+	lrpt_shard_report_t rep;
+	size_t nsym = 0;
+	int rc = lrpt_sharded_process(p, &plan, raw, nsamples, soft, cap, &nsym, &rep);
+	if (rc) { fprintf(stderr, "lrpt_sharded_process failed: %s\n", lrpt_strerror(rc)); return 1; }
+	struct egress eg;
+	memset(&eg, 0, sizeof(eg));
+	eg.out = out;
+	egress_push(&eg, soft, nsym, rep.first_lock_symbol);
+	egress_finish(&eg, ref_tail);
+	if (!quiet)
+		printf("(100.0%%) %zu samples in %d chunks, %zu symbols (%.1f Hz nominal), worst boundary agreement %.4f%s, Locked: %s\n",
+		       nsamples, rep.nchunks, nsym, symrate, rep.min_agreement_final, rep.aligned ? "" : " (a chunk kept another lock point)",
+		       rep.first_lock_symbol >= 0 ? "Yes" : "No");
+	free(raw); free(soft);
+	return 0;
+}
+
 int
 main(int argc, char *argv[])
 {
 	float pll_bw = 1, symrate = 72000.0f, freq_max_delta = -1;
 	int rrc_order = 32, interp_factor = 5, quiet = 0, oqpsk = 0, batch = 0;
 	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0;
+	size_t shard = 0;
 	char *output_fname = NULL;
 	FILE *in, *out;
 	int c;
@@ -284,6 +327,7 @@ main(int argc, char *argv[])
 			case OPT_STDOUT: stdout_mode = 1; break;
 			case OPT_DEVICE: device = atoi(optarg); break;
 			case OPT_REFTAIL: ref_tail = 1; break;
+			case OPT_SHARD: shard = (size_t)human_to_float(optarg); break;
 			case 'b': pll_bw = human_to_float(optarg); break;
 			case 'B': batch = 1; break;
 			case 'd': freq_max_delta = human_to_float(optarg); break;
@@ -338,6 +382,13 @@ main(int argc, char *argv[])
 	p.samplerate = samplerate; p.symrate = (int)symrate;                     /* float -> int, main.c:187 */
 	p.interp_factor = interp_factor; p.rrc_order = rrc_order; p.oqpsk = oqpsk; p.bps = bps;
 	p.device = device; p.nstreams = 1; p.kernel = LRPT_KERNEL_AUTO;
+	if (shard) {
+		if (!quiet) printf("Input: %s, output: %s\n", argv[optind], output_fname);
+		int src = run_sharded(in, out, &p, shard, symrate, quiet, ref_tail);
+		if (out != stdout) fclose(out);
+		if (in != stdin) fclose(in);
+		return src;
+	}
 	lrpt_demod_t *h = NULL;
 	int rc = lrpt_create(&h, &p);
 	if (rc) { fprintf(stderr, "lrpt_create failed: %s\n", lrpt_strerror(rc)); return 1; }

@@ -212,6 +212,28 @@ int  lrpt_shard_gather_device(const int8_t *d_soft, size_t soft_stride, int nrow
                               const int32_t *d_len, const int64_t *d_off, const int32_t *d_turns, int8_t *d_out,
                               void *cuda_stream);
 
+/*
+ * ONE recording time-sharded over the lanes of one GPU in a single call (csrc/shard_run.cu; HOST buffers;
+ * replaces the whole loop main.c:303-317 for an offline file, at STATISTICAL parity): the stream is cut into
+ * chunks of `chunk` samples that run as the streams of a batch -- `warm` samples of warm-up before each
+ * chunk, `overlap` samples into its successor (all multiples of 8; chunk + warm + overlap >= ~400 k samples
+ * keeps the share of symbols off by more than one LSB at the 0.3-0.4 % of the reference's own FMA/strict
+ * builds). The first two chunks are bit-exact. QPSK only; p->nstreams is ignored.
+ * soft: 2 int8 per symbol, ALL symbols in stream order (the host applies the 512-symbol lock gating with
+ * rep->first_lock_symbol, which is chunk 0's: -1 if the loop had not locked by the end of chunk 0).
+ */
+typedef struct lrpt_shard_plan { uint64_t chunk, warm, overlap; } lrpt_shard_plan_t;
+typedef struct lrpt_shard_report {
+	int32_t nchunks, launches;
+	float   min_agreement_scan;    /* worst boundary of the quadrant scan: share of overlap symbols agreeing  */
+	float   min_agreement_final;   /* worst boundary of the final join                                          */
+	int32_t aligned;               /* 1: every final boundary needed no turn (all chunks at one lock point)   */
+	int32_t reserved;
+	int64_t first_lock_symbol;
+} lrpt_shard_report_t;
+int  lrpt_sharded_process(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
+                          int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep);
+
 /* ---- introspection -------------------------------------------------------------- */
 /*
  * Host-only (needs no CUDA device): what lrpt_create derives from `p`, exactly as

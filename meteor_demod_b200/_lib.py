@@ -37,6 +37,16 @@ class Status(C.Structure):
                 ("nsamples", C.c_int64), ("nsymbols", C.c_int64), ("first_lock_symbol", C.c_int64)]
 
 
+class ShardPlan(C.Structure):
+    _fields_ = [("chunk", C.c_uint64), ("warm", C.c_uint64), ("overlap", C.c_uint64)]
+
+
+class ShardReport(C.Structure):
+    _fields_ = [("nchunks", C.c_int32), ("launches", C.c_int32), ("min_agreement_scan", C.c_float),
+                ("min_agreement_final", C.c_float), ("aligned", C.c_int32), ("reserved", C.c_int32),
+                ("first_lock_symbol", C.c_int64)]
+
+
 # name -> (restype, argtypes); one entry per symbol include/lrpt_b200.h declares
 SYMBOLS = {
     "lrpt_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Params)]),
@@ -70,6 +80,8 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrpt_shard_gather_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lrpt_sharded_process": (C.c_int, [C.POINTER(Params), C.POINTER(ShardPlan), C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(ShardReport)]),
     "lrpt_describe": (C.c_int, [C.POINTER(Params), C.POINTER(State), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lrpt_get_taps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lrpt_get_tanh_lut": (C.c_int, [C.c_void_p, C.c_void_p]),

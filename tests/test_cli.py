@@ -131,3 +131,26 @@ def test_several_recordings_as_one_batch(host, oracle_mod, tmp_path):
     odd.write_bytes(synth.wav_header(8, bps=8) + b"\x80" * 8)
     r = subprocess.run([host, "-B", "-q", str(wavs[0]), str(odd)], capture_output=True)
     assert r.returncode == 1 and b"one batch needs one format" in r.stderr
+
+
+def test_shard_flag_one_long_recording(host, oracle_mod, tmp_path):
+    """--shard: the recording is cut into chunks that run side by side (lrpt_sharded_process). Output = the library
+    call's symbols under the reference's egress rules; against the sequential reference run it has the same
+    number of symbols, an exact head (chunks 0 and 1) and a small share of symbols off by more than one LSB."""
+    from meteor_demod_b200 import egress, sharded, synth
+    raw = synth.make_raw(1_700_123, cfo_hz=45.0, seed=77)
+    wav = tmp_path / "long.wav"
+    wav.write_bytes(synth.wav_header(raw.nbytes) + raw.tobytes())
+    out = tmp_path / "long.s"
+    r = run([host, "-B", "--shard", "400k", "-o", str(out), str(wav)])
+    assert b"4 chunks" in r.stdout and b"Locked: Yes" in r.stdout
+    n = egress.consumed_samples(raw.nbytes, 16)
+    soft, rep = sharded.process_host(raw[: 2 * n], chunk=400_000, warm=150_000, overlap=8192, symrate=72000, bps=16)
+    got = out.read_bytes()
+    assert got == egress.gate(soft, rep["first_lock_symbol"])
+    w = oracle_mod.Oracle(bps=16).process(raw[: 2 * n])
+    assert soft.shape[0] == w.nsym and rep["first_lock_symbol"] == int(np.argmax(w.lock_once))
+    head = int((150_000 + 2 * 400_000) * 72000 / 230000) - 16
+    assert np.array_equal(soft[:head], w.soft[:head])
+    d = np.abs(soft.astype(np.int16) - w.soft.astype(np.int16)).max(axis=1)
+    assert (d > 1).mean() < 0.01

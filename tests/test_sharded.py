@@ -404,3 +404,39 @@ def test_long_stream_windows_are_consistent():
     for first, total in ((0, 5000), (4096, 4096), (5000, 9000), (12_345, 10_655), (19_999, 50), (20_000, 10)):
         win = synth.device_long_stream(per, n, total=total, device="cpu", block=4096, first=first)
         assert torch.equal(win, full[2 * first: 2 * (first + total)]), (first, total)
+
+
+@pytest.mark.gpu
+def test_single_call_c_entry_point_equals_python_handoff(stream, lib):
+    """lrpt_sharded_process (host buffer in, stitched symbols out, no Python in the loop) against the torch-
+    orchestrated hand-off run on the same plan: same kernels, same arithmetic, so byte-identical; plus its
+    report, the one-chunk case (exact) and argument checks."""
+    from meteor_demod_b200 import LrptError, sharded
+    from oracle import pyoracle
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    raw = torch.zeros(2 * plan.padded, dtype=torch.int16, device="cuda")
+    raw[: stream.size] = torch.from_numpy(stream).cuda()
+    want = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
+                                 rrc_order=32, interp_factor=5, handoff=True)
+    got, rep = sharded.process_host(stream, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
+                                    rrc_order=32, interp_factor=5)
+    assert np.array_equal(got, want["soft"].cpu().numpy())
+    assert rep["nchunks"] == plan.nchunks and rep["launches"] == 3 and rep["aligned"] == 1
+    assert abs(rep["min_agreement_final"] - float(want["agreement"].min())) < 1e-6
+    assert abs(rep["min_agreement_scan"] - float(want["first_pass"]["agreement"].min())) < 1e-6
+    seq = pyoracle.Oracle(**CFG).process(stream, want_float=False)
+    assert rep["first_lock_symbol"] == (int(np.argmax(seq.lock_once)) if seq.lock_once.any() else -1)
+    # a recording shorter than warm-up + one chunk is one chunk: the sequential run itself
+    short = stream[: 2 * 300_000]
+    got1, rep1 = sharded.process_host(short, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
+    w1 = pyoracle.Oracle(**CFG).process(short, want_float=False)
+    assert rep1["nchunks"] == 1 and np.array_equal(got1, w1.soft)
+    # a stream that ends inside chunk 1's overlap: nothing from the zero padding
+    n2 = WARM + CHUNK + 5000
+    got2, rep2 = sharded.process_host(stream[: 2 * n2], chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
+    w2 = pyoracle.Oracle(**CFG).process(stream[: 2 * n2], want_float=False)
+    assert rep2["nchunks"] == 2 and np.array_equal(got2, w2.soft)          # chunks 0 and 1 are exact
+    with pytest.raises(LrptError):
+        sharded.process_host(stream, chunk=CHUNK + 4, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
+    with pytest.raises(LrptError):
+        sharded.process_host(stream, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16, oqpsk=True)
