@@ -534,6 +534,29 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
                 "min_boundary_agreement": float(agree.item()), "tier_s": eps, "clocks": clk.summary()}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if world == 1 and not a.no_e2e:
+            # end to end through the single C call a host makes (lrpt_sharded_process, what host/lrpt_demod --shard
+            # runs): the recording in pinned HOST memory, H2D + three passes + join + D2H of the symbols inside
+            # the timed region, device buffers allocated and freed by the call. Bounded to 1 GSample of host memory.
+            ne = min(N, 1 << 30)
+            host = torch.empty(2 * ne, dtype=raw.dtype, pin_memory=True)
+            host.copy_(raw[: 2 * ne])
+            torch.cuda.synchronize()
+            hn = host.numpy()
+            kwe = dict(chunk=a.chunk, warm=a.warm, overlap=8192, symrate=symrate, bps=bps, rrc_order=order,
+                       interp_factor=interp, device=local)
+            sd.close()
+            del raw
+            torch.cuda.empty_cache()
+            soft_e, rep_e = sharded.process_host(hn, **kwe)          # warm-up (module load, first allocations)
+            reps, t0 = max(1, min(a.steps, 3)), time.perf_counter()
+            for _ in range(reps):
+                soft_e, rep_e = sharded.process_host(hn, **kwe)
+            dt = (time.perf_counter() - t0) / reps
+            line["e2e"] = {"value": ne / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3, "samples": int(ne),
+                           "h2d_bytes_per_step": int(ne * (bps // 4)), "d2h_bytes_per_step": int(2 * soft_e.shape[0]),
+                           "api": "lrpt_sharded_process (host buffers)", "nchunks": rep_e["nchunks"],
+                           "matches_device_path": bool(ne != N or np.array_equal(soft_e, res["soft"].cpu().numpy()))}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -177,20 +177,36 @@ template <> struct RawT<32> {
 	LRPT_DEV static elem zero() { return make_float2(0.f, 0.f); }
 };
 
-/* What the window holds: the raw element (WF = false: smallest footprint, converted at every tap)
- * or the float pair it converts to (WF = true: converted once per sample when its tile is appended,
- * 8 bytes per entry, so fewer warps fit but a tap costs three instructions less). */
-template <int BPS, bool WF> struct WinT {
+/* 8-bit samples as a bfloat16 pair: an integer in [-128, 127] has at most 8 significant bits, so it IS a
+ * bfloat16, and a bfloat16 becomes the float of the same value by a 16-bit shift -- one integer operation
+ * per component and no subtraction (a tap costs 5.75 instructions instead of 6.75), for 4 bytes per entry. */
+struct FmtBF16 {
+	typedef uint32_t elem;                       /* I in the low half, Q in the high half */
+	LRPT_DEV static float2 cvt(elem e) { return make_float2(__uint_as_float(e << 16), __uint_as_float(e & 0xffff0000u)); }
+	LRPT_DEV static f32x2_t cvt2(elem e) { return pk2(__uint_as_float(e << 16), __uint_as_float(e & 0xffff0000u)); }
+	LRPT_DEV static elem from_float(float2 v) { return __byte_perm(__float_as_uint(v.x), __float_as_uint(v.y), 0x7632); }
+};
+
+/* What the window holds (WF): 0 the raw element (smallest footprint, converted at every tap), 1 the float
+ * pair it converts to (converted once per sample when its tile is appended; 8 bytes per entry, so fewer
+ * warps fit, but a tap costs three instructions less), 2 (8-bit input only) a bfloat16 pair. */
+template <int BPS, int WF> struct WinT {
 	typedef RawT<BPS> W;                          /* format the FIR reads */
 	typedef typename RawT<BPS>::elem elem;
-	static constexpr int WBPS = BPS;
+	static constexpr int WBPS = BPS;              /* bytes per entry * 4 */
 	LRPT_DEV static elem from_raw(typename RawT<BPS>::elem e) { return e; }
 };
-template <int BPS> struct WinT<BPS, true> {
+template <int BPS> struct WinT<BPS, 1> {
 	typedef RawT<32> W;
 	typedef float2 elem;
 	static constexpr int WBPS = 32;
 	LRPT_DEV static elem from_raw(typename RawT<BPS>::elem e) { return RawT<BPS>::cvt(e); }
+};
+template <> struct WinT<8, 2> {
+	typedef FmtBF16 W;
+	typedef uint32_t elem;
+	static constexpr int WBPS = 16;
+	LRPT_DEV static elem from_raw(RawT<8>::elem e) { return FmtBF16::from_float(RawT<8>::cvt(e)); }
 };
 
 /* One FULL tile (LN_T samples starting at s0) of a lane's row into registers. */
@@ -204,7 +220,7 @@ LRPT_DEV void tile_load(const uint8_t *row, int s0, uint4 (&pf)[RawT<BPS>::NV])
 }
 
 /* The last, partial tile goes from global memory to the window element by element. */
-template <int BPS, bool WF>
+template <int BPS, int WF>
 LRPT_DEV void tile_copy_partial(typename WinT<BPS, WF>::elem *col, int e0, const uint8_t *row, int s0, int nsamples)
 {
 	typedef RawT<BPS> R;
@@ -214,7 +230,7 @@ LRPT_DEV void tile_copy_partial(typename WinT<BPS, WF>::elem *col, int e0, const
 }
 
 /* Registers -> window entries [e0, e0+LN_T) of this lane's column. */
-template <int BPS, bool WF>
+template <int BPS, int WF>
 LRPT_DEV void tile_store(typename WinT<BPS, WF>::elem *col, int e0, const uint4 (&pf)[RawT<BPS>::NV])
 {
 	typedef RawT<BPS> R;
@@ -237,10 +253,9 @@ LRPT_DEV void tile_store(typename WinT<BPS, WF>::elem *col, int e0, const uint4 
 #else
 #define LN_TAP(X, H) do { const float2 x_ = R::cvt(X); ar = __fadd_rn(ar, __fmul_rn(x_.x, (H))); ai = __fadd_rn(ai, __fmul_rn(x_.y, (H))); } while (0)
 #endif
-template <int BPS>
-LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb, int taps, float one)
+template <class R>
+LRPT_DEV float2 fir_lazy(const typename R::elem *__restrict__ w, const float *__restrict__ hb, int taps, float one)
 {
-	typedef RawT<BPS> R;
 #if LRPT_LANE_PACKED
 	f32x2_t acc = pk2(0.0f, 0.0f);
 	const f32x2_t one2 = pk2(one, one);
@@ -275,12 +290,11 @@ LRPT_DEV float2 fir_lazy(const typename RawT<BPS>::elem *__restrict__ w, const f
 /* The same filter with the DEFERRED half of the previous symbol step (demod_core.cuh, "split in two")
  * placed in the basic block of the first 64 taps: ptxas interleaves its long double-precision
  * chains with the issue-bound tap arithmetic, so they no longer cost time of their own. */
-template <int BPS, bool OQ>
-LRPT_DEV float2 fir_lazy_with_deferred(const typename RawT<BPS>::elem *__restrict__ w, const float *__restrict__ hb,
+template <class R, bool OQ>
+LRPT_DEV float2 fir_lazy_with_deferred(const typename R::elem *__restrict__ w, const float *__restrict__ hb,
                                        int taps, float one, Loop &r, const lrpt_consts_t &c, const float *lut,
                                        const Pend &pd, Osc &next, bool &ok)
 {
-	typedef RawT<BPS> R;
 #if LRPT_LANE_PACKED
 	f32x2_t acc = pk2(0.0f, 0.0f);
 	const f32x2_t one2 = pk2(one, one);
@@ -327,7 +341,7 @@ LRPT_DEV float2 fir_lazy_with_deferred(const typename RawT<BPS>::elem *__restric
 
 /* ------------------------------------------------------------- kernel ------ */
 
-template <bool OQ, int BPS, bool AUX, bool WF>
+template <bool OQ, int BPS, bool AUX, int WF>
 __global__ void __launch_bounds__(32*LN_MAX_WARPS, 1)
 demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 {
@@ -335,7 +349,6 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 	typedef WinT<BPS, WF> WT;
 	typedef typename WT::W WR;                                      /* the window's format */
 	typedef typename WT::elem elem;
-	constexpr int WBPS = WT::WBPS;
 	constexpr int T = LN_T;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -428,7 +441,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				const float s_gain = r.gain, s_pp = r.p_phase, s_pf = r.p_freq, s_pe = r.p_err;
 				const int s_lk = r.locked, s_lo = r.locked_once, s_ud = r.updown;
 				Osc next; bool ok;
-				const float2 y = fir_lazy_with_deferred<WBPS, OQ>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one,
+				const float2 y = fir_lazy_with_deferred<WR, OQ>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one,
 				                                                 r, c, lut, pd, next, ok);
 				if (!(ok && pend)) {                                 /* rare: nothing was outstanding (first event of the
 				                                                        launch), or a shortcut was not provably exact */
@@ -451,7 +464,7 @@ demod_lane_kernel(const lrpt_consts_t c, const LaneArgs a)
 				step_critical<OQ>(r, c, half, y.x, y.y, osc.s, osc.co, pd);
 				pend = true; pd_q = Qx;
 #else
-				const float2 y = fir_lazy<WBPS>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one);
+				const float2 y = fir_lazy<WR>(col + (te*T + nr)*32, hT + (L - 1 - i)*a.TS, taps, a.one);
 				const Loop saved = r;
 				float ore, oim; bool emitted; Osc next;
 				if (!symbol_fast_osc<OQ>(r, c, lut, half, y.x, y.y, osc, ore, oim, emitted, next)) {
@@ -550,15 +563,19 @@ bool lane_supported(const lrpt_consts_t &c)
 	return ln_fixed_smem(c.taps, c.interp) + ln_warp_smem(c.taps, 1, c.bps) <= (size_t)232448;
 }
 
-template <bool OQ, int BPS> static cudaError_t ln_attr1()
+template <bool OQ, int BPS, int WF> static cudaError_t ln_attr2()
 {
-	cudaError_t e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	cudaError_t e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false, WF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
 	if (e) return e;
-	e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
-	if (e || BPS == 32) return e;
-	e = cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, false, BPS != 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
-	if (e) return e;
-	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true, BPS != 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+	return cudaFuncSetAttribute(demod_lane_kernel<OQ, BPS, true, WF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_max_smem);
+}
+
+template <bool OQ> static cudaError_t ln_attr1()
+{
+	cudaError_t e;
+	if ((e = ln_attr2<OQ, 32, 0>()) || (e = ln_attr2<OQ, 16, 0>()) || (e = ln_attr2<OQ, 16, 1>()) ||
+	    (e = ln_attr2<OQ, 8, 0>()) || (e = ln_attr2<OQ, 8, 1>()) || (e = ln_attr2<OQ, 8, 2>())) return e;
+	return cudaSuccess;
 }
 
 cudaError_t lane_prepare(int device)
@@ -566,20 +583,19 @@ cudaError_t lane_prepare(int device)
 	cudaError_t e;
 	if ((e = cudaDeviceGetAttribute(&ln_num_sms, cudaDevAttrMultiProcessorCount, device))) return e;
 	if ((e = cudaDeviceGetAttribute(&ln_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device))) return e;
-	if ((e = ln_attr1<false, 8>()) || (e = ln_attr1<false, 16>()) || (e = ln_attr1<false, 32>()) ||
-	    (e = ln_attr1<true, 8>()) || (e = ln_attr1<true, 16>()) || (e = ln_attr1<true, 32>())) return e;
+	if ((e = ln_attr1<false>()) || (e = ln_attr1<true>())) return e;
 	return cudaSuccess;
 }
 
-template <bool OQ> static void ln_launch1(const lrpt_consts_t &c, const LaneArgs &w, int blocks, size_t smem, cudaStream_t st, bool wf)
+template <bool OQ> static void ln_launch1(const lrpt_consts_t &c, const LaneArgs &w, int blocks, size_t smem, cudaStream_t st, int wf)
 {
 	const int threads = 32*w.W;
 	const bool aux = w.symf || w.symq;                              /* optional float / index side outputs */
 #define LN_GO(B, F) do { if (aux) demod_lane_kernel<OQ, B, true, F><<<blocks, threads, smem, st>>>(c, w); \
                          else     demod_lane_kernel<OQ, B, false, F><<<blocks, threads, smem, st>>>(c, w); } while (0)
-	if (c.bps == 16)     { if (wf) LN_GO(16, true); else LN_GO(16, false); }
-	else if (c.bps == 8) { if (wf) LN_GO(8, true);  else LN_GO(8, false); }
-	else                 LN_GO(32, false);
+	if (c.bps == 16)     { if (wf == 1) LN_GO(16, 1); else LN_GO(16, 0); }
+	else if (c.bps == 8) { if (wf == 1) LN_GO(8, 1); else if (wf == 2) LN_GO(8, 2); else LN_GO(8, 0); }
+	else                 LN_GO(32, 0);
 #undef LN_GO
 }
 
@@ -603,17 +619,22 @@ static bool ln_plan(int nwarps, int taps, int L, int wbps, int &W, int &NT)
 	return true;
 }
 
-/* Window format for a launch. Float pairs cost three instructions less per tap but twice (s16) or four
- * times (u8) the shared memory; measured (tools/ab_wf.py, B200): +2..10 % when the same number of warps
- * per SM fits either way, -18 % when the float window halves them. So: float pairs exactly when they
- * do not cost a warp. LRPT_LANE_WF=0/1 overrides (A/B runs, tests). */
-static bool ln_float_window(const lrpt_consts_t &c, int nwarps)
+/* Window format for a launch (WinT). A wider entry saves instructions per tap (float pairs three, bfloat16
+ * pairs one) but costs shared memory; measured (tools/ab_wf.py, B200): float pairs +2..10 % when the same
+ * number of warps per SM fits either way, -18 % when they halve it. So: the widest format that does not
+ * cost a warp. LRPT_LANE_WF=0/1/2 overrides (A/B runs, tests). */
+static int ln_window_format(const lrpt_consts_t &c, int nwarps)
 {
-	if (c.bps == 32) return false;
-	if (const char *e = getenv("LRPT_LANE_WF")) return atoi(e) != 0;
+	if (c.bps == 32) return 0;
+	if (const char *e = getenv("LRPT_LANE_WF")) {
+		const int v = atoi(e);
+		return (v == 1 || (v == 2 && c.bps == 8)) ? v : 0;
+	}
 	int Wr, NTr, Wf, NTf;
-	if (!ln_plan(nwarps, c.taps, c.interp, c.bps, Wr, NTr) || !ln_plan(nwarps, c.taps, c.interp, 32, Wf, NTf)) return false;
-	return Wf == Wr && NTf >= 2;
+	if (!ln_plan(nwarps, c.taps, c.interp, c.bps, Wr, NTr)) return 0;
+	if (ln_plan(nwarps, c.taps, c.interp, 32, Wf, NTf) && Wf == Wr && NTf >= 2) return 1;
+	if (c.bps == 8 && ln_plan(nwarps, c.taps, c.interp, 16, Wf, NTf) && Wf == Wr && NTf >= 2) return 2;
+	return 0;
 }
 
 cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
@@ -621,14 +642,14 @@ cudaError_t launch_lane(const LaunchArgs &a, cudaStream_t st, int *launches)
 	const lrpt_consts_t &c = *a.c;
 	const int L = c.interp, taps = c.taps;
 	const int nwarps = (a.nstreams + 31)/32;
-	const bool wf = ln_float_window(c, nwarps);
-	const int wbps = wf ? 32 : c.bps;                               /* window entry: wbps/4 bytes */
+	const int wf = ln_window_format(c, nwarps);
+	const int wbps = wf == 1 ? 32 : wf == 2 ? 16 : c.bps;           /* window entry: wbps/4 bytes */
 	const size_t fixed = ln_fixed_smem(taps, L);
 	int W, NT;
 	if (!ln_plan(nwarps, taps, L, wbps, W, NT)) return cudaErrorInvalidConfiguration;
 	const int blocks = (nwarps + W - 1)/W;
 	const size_t smem = fixed + W*ln_warp_smem(taps, NT, wbps);
-	if (getenv("LRPT_LANE_DEBUG")) fprintf(stderr, "lane: streams %d W %d NT %d blocks %d smem %zu wf %d\n", a.nstreams, W, NT, blocks, smem, (int)wf);
+	if (getenv("LRPT_LANE_DEBUG")) fprintf(stderr, "lane: streams %d W %d NT %d blocks %d smem %zu wf %d\n", a.nstreams, W, NT, blocks, smem, wf);
 
 	int n = 0;
 	size_t done = 0;

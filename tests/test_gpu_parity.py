@@ -274,14 +274,16 @@ def test_lane_kernel_many_warps_per_sm(name, oracle_mod, lib):
         assert_state_equal(d.state(s), o)
 
 
-@pytest.mark.parametrize("wf", ["0", "1"])
+@pytest.mark.parametrize("wf", ["0", "1", "2"])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
 def test_lane_window_formats(name, wf, oracle_mod, lib, monkeypatch):
-    """The lane kernel's delay-line window in the input's own type (LRPT_LANE_WF=0) and as float pairs
-    (=1; what the launch picks by itself when it costs no warp): both bit-exact, ragged launches, 70 streams
-    (3 warps, idle lanes in the last), float symbols and state included."""
-    monkeypatch.setenv("LRPT_LANE_WF", wf)
+    """The lane kernel's delay-line window in the input's own type (LRPT_LANE_WF=0), as float pairs (=1) and,
+    for 8-bit input, as bfloat16 pairs (=2) -- the launch picks the widest that costs no warp: all bit-exact,
+    ragged launches, 70 streams (3 warps, idle lanes in the last), float symbols and state included."""
     cfg = CONFIGS[name]
+    if wf == "2" and cfg["bps"] != 8:
+        pytest.skip("bfloat16 pairs hold 8-bit samples only")
+    monkeypatch.setenv("LRPT_LANE_WF", wf)
     n = 40_000
     raw = np.stack([make_case(name, n, seed=400 + s, cfo_hz=-600.0 + 17 * s) for s in range(7)])
     raw = np.concatenate([raw] * 10)

@@ -25,7 +25,7 @@ def run(raw, B, N, env, order=32, L=5, oqpsk=0, symrate=72000, bps=16, reps=3):
     d.close()
     return soft, c
 
-if __name__ == "__main__":
+if __name__ == "__main__":  # noqa
     os.environ["LRPT_LANE_DEBUG"] = "1"
     per = synth.baseband(230000, periodic=True).astype(np.complex64)
     N = 32768
