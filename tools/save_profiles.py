@@ -34,7 +34,7 @@ want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dra
         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
 with open('profiles/r1_lane_kernel_ncu_raw.csv', 'w') as f:
     f.write("# ncu --set full --clock-control none --import-source on -k regex:demod_lane -s 1 -c 1 python tools/prof_one.py 75776 32768 32 5 0 lane\n")
-    f.write("# one launch of lrpt::demod_lane_kernel<false,16,false>: 75776 streams x 32768 samples, QPSK 72k s16 RRC-32 x5 (selected raw metrics)\n")
+    f.write("# one launch of lrpt::demod_lane_kernel<OQ=false, BPS=16, AUX=false, WF=0 (raw-typed window)>: 75776 streams x 32768 samples, QPSK 72k s16 RRC-32 x5 (selected raw metrics)\n")
     f.write("metric,unit,value\n")
     for i, h in enumerate(hdr):
         if h in want:
