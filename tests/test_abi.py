@@ -83,3 +83,22 @@ def test_egress_gating_rules():
     prev = soft[512:1024].reshape(-1)
     assert np.array_equal(stale[: 1024 - tail.size], prev[tail.size:1024][: stale.size])
     assert egress.consumed_samples(100000, 16) == 3 * 32768 // 4
+
+
+def test_sharded_entry_point_checks_arguments_and_needs_a_gpu(lib):
+    """lrpt_sharded_process: argument errors are reported before any CUDA call; without a device the call fails
+    with LRPT_ERR_CUDA (no CPU path). Skipped parts aside, no compute happens here."""
+    import pytest
+    import torch
+    from meteor_demod_b200 import LrptError, sharded
+    raw = np.zeros(2 * 4096, np.int16)
+    for bad in (dict(chunk=1001), dict(warm=12), dict(overlap=0), dict(oqpsk=True), dict(bps=12)):
+        kw = dict(chunk=1024, warm=512, overlap=64, symrate=72000, bps=16)
+        kw.update(bad)
+        with pytest.raises(LrptError) as e:
+            sharded.process_host(raw, **kw)
+        assert e.value.code == -1, bad
+    if not torch.cuda.is_available():
+        with pytest.raises(LrptError) as e:
+            sharded.process_host(raw, chunk=1024, warm=512, overlap=64, symrate=72000, bps=16)
+        assert e.value.code == -2
