@@ -21,9 +21,11 @@
  *   join    cut points mid-way between symbols, runs gathered in stream order
  */
 #include <cuda_runtime.h>
+#include <chrono>
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -47,6 +49,20 @@ size_t symbol_capacity(size_t nsamples, const lrpt_params_t &p)
 {
 	return (size_t)((double)nsamples*((double)p.symrate/(double)p.samplerate)*1.02) + 64;
 }
+
+/* LRPT_SHARD_TIMING=1: wall time of every phase on stderr (device work is synchronised at each mark) */
+struct Phases {
+	bool on = getenv("LRPT_SHARD_TIMING") != nullptr;
+	std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+	void mark(const char *what)
+	{
+		if (!on) return;
+		cudaDeviceSynchronize();
+		const auto n = std::chrono::steady_clock::now();
+		fprintf(stderr, "lrpt_sharded_process: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+		t = n;
+	}
+};
 
 #define CK(x) do { if ((x) != cudaSuccess) return LRPT_ERR_CUDA; } while (0)
 #define RC(x) do { const int rc_ = (x); if (rc_) return rc_; } while (0)
@@ -99,6 +115,7 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	*nsym = 0;
 	CK(cudaSetDevice(params->device));
 
+	Phases ph;
 	lrpt_params_t p = *params;
 	p.nstreams = (int32_t)M;
 	Handle hd;
@@ -120,8 +137,10 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	DevBuf d_raw, d_soft, d_q, d_nsym, d_cnt, d_base, d_states;
 	CK(d_raw.alloc(padded*bytes)); CK(d_soft.alloc(M*2*cap_row)); CK(d_q.alloc(M*4*cap_row)); CK(d_nsym.alloc(4*M));
 	CK(d_cnt.alloc(4*M)); CK(d_base.alloc(8*M));
-	CK(cudaMemset(d_raw.p, 0, padded*bytes));
+	ph.mark("handle + device buffers");
+	CK(cudaMemset(d_raw.as<char>() + nsamples*bytes, 0, (padded - nsamples)*bytes));
 	CK(cudaMemcpy(d_raw.p, raw_iq, nsamples*bytes, cudaMemcpyHostToDevice));
+	ph.mark("H2D of the recording");
 	RC(lrpt_set_symbol_index_output(h, d_q.as<uint32_t>(), 4*cap_row));
 	const char *raw0 = d_raw.as<char>();
 	const size_t soft_stride = 2*cap_row, q_stride = 4*cap_row;
@@ -147,8 +166,10 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 		CK(cudaMemcpy(soft, d_soft.p, 2*(size_t)counts[0], cudaMemcpyDeviceToHost));
 		out_n = counts[0];
 	}
+	ph.mark("pass A (warm-up)");
 	/* pass B: owned + overlap, from the live state */
 	RC(run_pass(W, n_row));
+	ph.mark("pass B");
 	std::vector<int64_t> target(M - 1), cut;
 	std::vector<int32_t> k;
 	std::vector<float> agree;
@@ -176,6 +197,7 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 		r.first_lock_symbol = s.first_lock_symbol;                  /* chunk 0 counts its symbols as the stream does */
 	}
 
+	ph.mark("quadrant scan + chunk 0");
 	/* hand-off: row c starts pass C from row c-1's end state, its Costas NCO turned back K[c-1] quarter turns
 	 * (p_phase = (float)((double)p_phase - K*pi/2), as lrpt_restore does; pll.c:16) */
 	{
@@ -200,8 +222,10 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 		RC(lrpt_sync(h, nullptr));
 	}
 
+	ph.mark("state hand-off");
 	/* pass C, then the join of rows 1 .. M-1 (rows 0 and 1 are one exact trajectory: nothing is cut off row 1's front) */
 	RC(run_pass(W + V, n_row));
+	ph.mark("pass C");
 	const int n = (int)M - 1;
 	const int8_t *soft1 = d_soft.as<int8_t>() + soft_stride;
 	const uint32_t *q1 = reinterpret_cast<const uint32_t *>(d_q.as<char>() + q_stride);
@@ -239,7 +263,9 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	CK(cudaMemcpy(dturn.p, turns.data(), 4*(size_t)n, cudaMemcpyHostToDevice));
 	RC(lrpt_shard_gather_device(soft1, soft_stride, n, longest, dst.as<int32_t>(), dln.as<int32_t>(), doff.as<int64_t>(),
 	                            dturn.as<int32_t>(), dout.as<int8_t>(), nullptr));
+	ph.mark("join (scan, ranges, gather)");
 	CK(cudaMemcpy(soft + 2*out_n, dout.p, 2*total, cudaMemcpyDeviceToHost));   /* default stream: ordered after the gather */
+	ph.mark("D2H of the symbols");
 	out_n += total;
 	*nsym = out_n;
 	r.launches = (int32_t)lrpt_launch_count(h);

@@ -555,18 +555,26 @@ def demod_sharded(raw, nsamples, **kw):
         sd.close()
 
 
-def process_host(raw, chunk=1 << 18, warm=150000, overlap=8192, **cfg):
+def process_host(raw, chunk=1 << 18, warm=150000, overlap=8192, out=None, **cfg):
     """ONE recording in host memory, time-sharded on one GPU by a single C call (lrpt_sharded_process,
     csrc/shard_run.cu -- the hand-off scheme above without Python in the loop; what host/lrpt_demod --shard
     uses). raw: numpy array of interleaved I,Q in the configured sample format. cfg: make_params' keywords
-    (symrate, bps, rrc_order, interp_factor, ...). Returns (soft [n,2] int8, report dict)."""
+    (symrate, bps, rrc_order, interp_factor, ...). out: optional int8 array [cap, 2] to receive the symbols
+    (page-locked memory makes the final copy 15x faster than a fresh pageable array). Returns (soft [n,2]
+    int8 -- a view of `out` when given --, report dict)."""
     from ._lib import LrptError, ShardPlan, ShardReport, load
     from .demod import make_params, symbol_capacity
     p = make_params(**cfg)
     a = np.ascontiguousarray(raw).reshape(-1)
     n = a.size // 2
     cap = symbol_capacity(n, p.samplerate, p.symrate)
-    soft = np.empty((cap, 2), np.int8)
+    if out is None:
+        soft = np.empty((cap, 2), np.int8)
+    else:
+        soft = out
+        if soft.dtype != np.int8 or not soft.flags["C_CONTIGUOUS"] or soft.ndim != 2 or soft.shape[1] != 2:
+            raise ValueError("out must be a C-contiguous int8 array [cap, 2]")
+        cap = soft.shape[0]
     nsym, rep, plan = C.c_size_t(0), ShardReport(), ShardPlan(chunk, warm, overlap)
     rc = load().lrpt_sharded_process(C.byref(p), C.byref(plan), a.ctypes.data, n, soft.ctypes.data, cap,
                                      C.byref(nsym), C.byref(rep))

@@ -440,3 +440,50 @@ def test_single_call_c_entry_point_equals_python_handoff(stream, lib):
         sharded.process_host(stream, chunk=CHUNK + 4, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
     with pytest.raises(LrptError):
         sharded.process_host(stream, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16, oqpsk=True)
+
+
+@pytest.mark.gpu
+def test_stitch_kernels_equal_torch_ops_on_random_rows(lib):
+    """csrc/shard_stitch.cu against the torch formulation of the same join (boundary_quadrants / stitch with
+    absolute int64 indices) on random rows: ragged counts, random quarter turns per row, timing jitter, stale
+    entries behind the valid part, boundaries with few pairs."""
+    from meteor_demod_b200 import sharded
+    g = torch.Generator().manual_seed(5)
+    for trial, (M, C, V, L) in enumerate(((9, 4000, 512, 5), (3, 900, 96, 8), (40, 2500, 256, 3), (2, 700, 64, 5))):
+        plan = sharded.Plan(M * C + 300, C, 300, V, L)
+        M = plan.nchunks
+        n_row = plan.n_main + V
+        cap = n_row * L // 14 + 40
+        truth = torch.randint(0, 4, (plan.padded * L // 14 + 8,), generator=g)      # the stream's symbols (quadrant per slot)
+        soft = torch.zeros((M, cap, 2), dtype=torch.int8)
+        q = torch.randint(0, 1 << 20, (M, cap), generator=g).to(torch.int32)          # stale garbage everywhere first
+        count = torch.zeros(M, dtype=torch.int64)
+        base = torch.tensor([plan.start(c) * L for c in range(M)], dtype=torch.int64)
+        turn = torch.randint(0, 4, (M,), generator=g)
+        for c in range(M):
+            slots = torch.arange((plan.start(c) * L + 13) // 14, (plan.start(c) + n_row) * L // 14)
+            slots = slots[: cap - int(torch.randint(0, 30, (1,), generator=g))]
+            n = slots.numel()
+            jit = torch.randint(-1, 2, (n,), generator=g)
+            q[c, :n] = (slots * 14 + 3 + jit - base[c]).clamp(min=0).to(torch.int32)
+            amp = torch.randint(20, 120, (n, 2), generator=g)
+            sgn = torch.tensor([[1, 1], [-1, 1], [-1, -1], [1, -1]])[truth[slots]]
+            noise = (torch.rand(n, 2, generator=g) < 0.03).long() * -2 + 1           # a few wrong hard decisions
+            s = (amp * sgn * noise).to(torch.int8)
+            soft[c, :n] = sharded.rotate_quarter_turns(s, int(-turn[c]) % 4)
+            count[c] = n
+        dsoft, dq, dcount, dbase = soft.cuda(), q.cuda(), count.cuda(), base.cuda()
+        q_abs = dq.to(torch.int64) + dbase[:, None]
+        Bq = torch.tensor([plan.cut_target(c) for c in range(1, M)], dtype=torch.int64, device="cuda")
+        k1, a1, c1 = sharded.boundary_quadrants(dsoft, dq, dcount, Bq, base=dbase)    # kernels
+        k0, a0, c0 = sharded.boundary_quadrants(dsoft, q_abs, dcount, Bq)              # torch ops
+        assert torch.equal(k1, k0) and torch.equal(c1, c0) and torch.allclose(a1, a0, atol=1e-6), trial
+        want_k = (turn[1:] - turn[:-1]) % 4
+        assert torch.equal(k0.cpu(), want_k), trial
+        r1 = sharded.stitch(dsoft, dq, dcount, plan, base=dbase)
+        r0 = sharded.stitch(dsoft, q_abs, dcount, plan)
+        assert torch.equal(r1["soft"], r0["soft"]) and r1["K_last"] == r0["K_last"], trial
+        # every slot of the stream exactly once, in order, turned back to row 0's lock point
+        got = r0["soft"].cpu()
+        nslots = (plan.nsamples * L - 1 - 3 + 1 + 13) // 14
+        assert got.shape[0] == nslots, (trial, got.shape[0], nslots)
