@@ -154,3 +154,27 @@ def test_shard_flag_one_long_recording(host, oracle_mod, tmp_path):
     assert np.array_equal(soft[:head], w.soft[:head])
     d = np.abs(soft.astype(np.int16) - w.soft.astype(np.int16)).max(axis=1)
     assert (d > 1).mean() < 0.01
+
+
+def test_live_pipe_is_demodulated_as_it_arrives(host, oracle_mod, tmp_path):
+    """A live source (rtl_sdr | lrpt_demod -): blocks are taken as they arrive instead of waiting for a full
+    16 MiB slab. Bursts with pauses, odd burst sizes: the output must be what one uninterrupted run gives,
+    and the first symbols must be on disk while the source is still open."""
+    import time
+    from meteor_demod_b200 import synth
+    raw = synth.make_raw(600_000, symrate=80000, oqpsk=True, bps=8, cfo_hz=60.0, seed=31).tobytes()
+    args = ["-m", "oqpsk", "-r", "80000", "--bps", "8", "-s", "230000", "-B", "-q"]
+    out = tmp_path / "live.s"
+    p = subprocess.Popen([host] + args + ["-o", str(out), "-"], stdin=subprocess.PIPE)
+    cuts = [0, 100_000, 100_001, 500_000, 900_037, len(raw)]
+    seen_early = False
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        p.stdin.write(raw[a:b])
+        p.stdin.flush()
+        time.sleep(0.4)
+        seen_early = seen_early or (out.exists() and out.stat().st_size > 0)
+    assert seen_early                                   # symbols were written before the pipe was closed
+    p.stdin.close()
+    assert p.wait(timeout=60) == 0
+    want, _ = expected(raw[44:], 8, oracle_mod, False, symrate=80000, oqpsk=1)
+    assert out.read_bytes() == want
