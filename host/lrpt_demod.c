@@ -22,9 +22,11 @@
  * streams of one batch (lrpt_process_batch; archive reprocessing) -- every file's output is what a
  * separate run on it writes, into <input>.s.
  */
+#include <errno.h>
 #include <getopt.h>
 #include <math.h>
 #include <poll.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -186,28 +188,37 @@ egress_finish(struct egress *e, int ref_tail)
 
 /* Whole 32 KiB blocks only: a trailing partial block is never consumed (wavfile.c:55). Returns the bytes
  * usable, at most `want` (a multiple of the block size). The first block is waited for; after that only
- * what has ALREADY arrived is taken, so a live source (rtl_sdr | lrpt_demod -, README.md:75 of the reference)
- * is demodulated block by block as it comes in -- 71 ms of signal at 230 kS/s 8-bit, like the reference's own
- * 32 KiB reads (wavfile.c:8,55) -- while a file or a fast pipe still fills whole slabs. */
+ * what has ALREADY arrived is taken (a partial block waits in `carry` for the next call), so a live source
+ * (rtl_sdr | lrpt_demod -, README.md:75 of the reference) is demodulated block by block as it comes in --
+ * 71 ms of signal at 230 kS/s 8-bit, like the reference's own 32 KiB reads (wavfile.c:8,55) -- while a file
+ * or a fast pipe still fills whole slabs. The stream must be unbuffered (setvbuf _IONBF): read() is used. */
+struct reader {
+	FILE *in;
+	int eof;
+	size_t ncarry;
+	uint8_t carry[FILE_BLOCK];
+};
+
 static size_t
-read_blocks(FILE *in, uint8_t *dst, size_t want, int *eof)
+read_blocks(struct reader *r, uint8_t *dst, size_t want)
 {
-	size_t got = 0;
-	*eof = 0;
-	while (got + FILE_BLOCK <= want) {
-		if (got) {
-			struct pollfd p = { fileno(in), POLLIN, 0 };
+	const int fd = fileno(r->in);
+	size_t got = r->ncarry;
+	memcpy(dst, r->carry, got);
+	r->ncarry = 0;
+	while (!r->eof && got < want) {
+		if (got >= FILE_BLOCK) {
+			struct pollfd p = { fd, POLLIN, 0 };
 			if (poll(&p, 1, 0) <= 0) break;                     /* nothing more right now */
 		}
-		size_t have = 0;
-		while (have < FILE_BLOCK) {
-			size_t r = fread(dst + got + have, 1, FILE_BLOCK - have, in);
-			if (!r) { *eof = 1; return got; }                   /* the partial block is dropped */
-			have += r;
-		}
-		got += FILE_BLOCK;
+		ssize_t n = read(fd, dst + got, want - got);
+		if (n < 0 && errno == EINTR) continue;
+		if (n <= 0) { r->eof = 1; break; }
+		got += (size_t)n;
 	}
-	return got;
+	const size_t whole = got/FILE_BLOCK*FILE_BLOCK;
+	if (!r->eof) { r->ncarry = got - whole; memcpy(r->carry, dst + whole, r->ncarry); }   /* else: the partial block is dropped */
+	return whole;
 }
 
 /* Several recordings as the streams of one batch. All share the command line's settings and must agree
@@ -216,15 +227,16 @@ read_blocks(FILE *in, uint8_t *dst, size_t want, int *eof)
 static int
 run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps_opt, float symrate, int quiet, int ref_tail)
 {
-	struct input { FILE *in; int eof; size_t avail; struct egress eg; lrpt_status_t last; } *f = calloc((size_t)nfiles, sizeof(*f));
+	struct input { struct reader rd; int open; size_t avail; struct egress eg; lrpt_status_t last; } *f = calloc((size_t)nfiles, sizeof(*f));
 	int samplerate = -1, bps = 0, i, rc, active = nfiles;
 	char path[4096];
 	if (!f) { fprintf(stderr, "out of memory\n"); return 1; }
 	for (i = 0; i < nfiles; i++) {
 		int sr = samplerate_opt, b = bps_opt;
-		if (!(f[i].in = fopen(names[i], "rb"))) { fprintf(stderr, "Could not open input file\n"); return 1; }
-		setvbuf(f[i].in, NULL, _IONBF, 0);
-		if (wav_parse(f[i].in, &sr, &b)) fseek(f[i].in, 0, SEEK_SET);
+		if (!(f[i].rd.in = fopen(names[i], "rb"))) { fprintf(stderr, "Could not open input file\n"); return 1; }
+		f[i].open = 1;
+		setvbuf(f[i].rd.in, NULL, _IONBF, 0);
+		if (wav_parse(f[i].rd.in, &sr, &b)) fseek(f[i].rd.in, 0, SEEK_SET);
 		if (sr < 0) { fprintf(stderr, "Could not auto-detect sample rate. Please specify it with -s <samplerate>\n"); return 1; }
 		if (!b) { fprintf(stderr, "Could not auto-detect bits per sample, assuming 16\n"); b = 16; }
 		if (i && (sr != samplerate || b != bps)) {
@@ -254,11 +266,11 @@ run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps
 		/* refill: every stream still open reads up to one slab; the call covers what ALL of them have */
 		size_t common = slab_bytes;
 		for (i = 0; i < nfiles; i++) {
-			if (!f[i].in) continue;
-			if (!f[i].avail && !f[i].eof) f[i].avail = read_blocks(f[i].in, raw + (size_t)i*slab_bytes, slab_bytes, &f[i].eof);
+			if (!f[i].open) continue;
+			if (!f[i].avail && !f[i].rd.eof) f[i].avail = read_blocks(&f[i].rd, raw + (size_t)i*slab_bytes, slab_bytes);
 			if (!f[i].avail) {                                  /* finished: final flush, then silence */
 				egress_finish(&f[i].eg, ref_tail);
-				fclose(f[i].eg.out); fclose(f[i].in); f[i].in = NULL; active--;
+				fclose(f[i].eg.out); fclose(f[i].rd.in); f[i].open = 0; active--;
 				memset(raw + (size_t)i*slab_bytes, bps == 8 ? 128 : 0, slab_bytes);
 				continue;
 			}
@@ -268,7 +280,7 @@ run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps
 		rc = lrpt_process_batch(h, raw, slab_bytes, common/bytes_per_sample, soft, 2*cap, cap, nsym, NULL, 0);
 		if (rc) { fprintf(stderr, "lrpt_process_batch failed: %s (%s)\n", lrpt_strerror(rc), lrpt_last_error(h)); return 1; }
 		for (i = 0; i < nfiles; i++) {
-			if (!f[i].in) continue;
+			if (!f[i].open) continue;
 			lrpt_status(h, i, &f[i].last);                      /* the stream's state while it still has input */
 			egress_push(&f[i].eg, soft + (size_t)i*2*cap, nsym[i], f[i].last.first_lock_symbol);
 			f[i].avail -= common;                               /* keep the unconsumed rest at the front of the row */
@@ -293,14 +305,16 @@ run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float sym
 {
 	size_t have = 0, room = (size_t)64 << 20;
 	uint8_t *raw = malloc(room);
-	int eof = 0;
-	while (raw && !eof) {
+	struct reader *rd = calloc(1, sizeof(*rd));
+	if (!rd) { fprintf(stderr, "out of memory\n"); return 1; }
+	rd->in = in;
+	while (raw && !rd->eof) {
 		if (room - have < (size_t)FILE_BLOCK*SLAB_BLOCKS) {
 			uint8_t *grown = realloc(raw, room *= 2);
 			if (!grown) { free(raw); raw = NULL; break; }
 			raw = grown;
 		}
-		have += read_blocks(in, raw + have, (size_t)FILE_BLOCK*SLAB_BLOCKS, &eof);
+		have += read_blocks(rd, raw + have, (size_t)FILE_BLOCK*SLAB_BLOCKS);
 	}
 	if (!raw) { fprintf(stderr, "out of memory\n"); return 1; }
 	const size_t nsamples = have/((size_t)p->bps/4);
@@ -429,9 +443,11 @@ main(int argc, char *argv[])
 	eg.out = out;
 	if (!raw || !soft) { fprintf(stderr, "out of memory\n"); return 1; }
 
+	struct reader *rd = calloc(1, sizeof(*rd));
+	if (!rd) { fprintf(stderr, "out of memory\n"); return 1; }
+	rd->in = in;
 	for (;;) {
-		int eof;
-		const size_t use = read_blocks(in, raw, slab_bytes, &eof);
+		const size_t use = read_blocks(rd, raw, slab_bytes);
 		if (!use) break;
 		size_t nsym = 0;
 		rc = lrpt_process(h, raw, use/bytes_per_sample, soft, cap, &nsym, &first_lock);
@@ -450,7 +466,7 @@ main(int argc, char *argv[])
 			fflush(stdout);
 			last_status = now_ms();
 		}
-		if (eof) break;
+		if (rd->eof) break;
 	}
 
 	egress_finish(&eg, ref_tail);
