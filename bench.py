@@ -430,16 +430,17 @@ def main():
     limiter = None                                          # what ncu says binds the kernel (committed capture)
     try:
         prof = {}
-        for ln in open(os.path.join(ROOT, "profiles", "r1_lane_kernel_ncu_raw.csv")):
+        prof_file = {"c1": "r1_lane_kernel_ncu_raw.csv", "c2": "r1_lane_kernel_c2_ncu_raw.csv"}.get(a.workload, "")
+        for ln in open(os.path.join(ROOT, "profiles", prof_file)):
             f = ln.strip().split(",")
             if len(f) == 3 and not ln.startswith("#"):
                 prof[f[0]] = f[2]
-        if a.workload == "c1" and d.kernel_name() == "lane":
+        if prof and d.kernel_name() == "lane" and B == 75776:
             limiter = {"resource": "warp instruction issue slots",
                        "issue_active_pct": float(prof["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
                        "fma_pipe_pct": float(prof["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
                        "alu_pipe_pct": float(prof["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]),
-                       "source": "profiles/r1_lane_kernel_ncu_raw.csv (ncu --set full, same kernel and workload)"}
+                       "source": "profiles/%s (ncu --set full, same kernel and workload)" % prof_file}
     except Exception:
         pass
     fir_flops = float(counts.sum()) * (2 if oqpsk else 1) * 4.0 * (2 * order + 1)   # one filter_get per (half-)symbol
