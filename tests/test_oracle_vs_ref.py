@@ -124,3 +124,58 @@ def test_quantiser(oracle_mod):
     for v, want in ((0.0, 0), (1.9, 0), (2.0, 1), (-1.9, 0), (-2.0, -1), (253.9, 126), (254.0, 127), (1e9, 127),
                     (-254.0, -127), (-1e9, -127), (3.99, 1), (-3.99, -1)):
         assert L.lrpt_oracle_quantise(v) == want, v
+
+
+def _same_run(o, r, raw):
+    a, b = o.process(raw), r.process(raw)
+    assert a.nsym == b.nsym
+    assert np.array_equal(bits(a.sym), bits(b.sym)) and np.array_equal(a.soft, b.soft)
+    assert np.array_equal(a.sample_idx, b.sample_idx) and np.array_equal(a.lock_once, b.lock_once)
+    assert np.array_equal(bits(o.history()), bits(r.history()))
+    so, sr = o.state(), r.state()
+    for k in ("t_prev", "t_phase", "t_freq", "agc_gain", "agc_bias_re", "agc_bias_im", "p_freq", "p_phase", "p_err"):
+        assert np.float32(so[k]).tobytes() == np.float32(sr[k]).tobytes(), k
+    return a.nsym
+
+
+def test_port_equals_reference_on_the_config5_grid(oracle_mod):
+    """BASELINE config 5 in full -- RRC order {16,32,64,128} x oversampling {3,5,8}, QPSK 72k s16 and OQPSK 80k
+    u8 -- port against the compiled reference on 120k samples per corner (taps, symbols, state, delay line)."""
+    need_ref(oracle_mod)
+    from meteor_demod_b200 import synth
+    for oq, symrate, bps in ((0, 72000, 16), (1, 80000, 8)):
+        raw = synth.make_raw(120_000, symrate=symrate, oqpsk=bool(oq), bps=bps, seed=8, cfo_hz=-333.0)
+        for order in (16, 32, 64, 128):
+            for interp in (3, 5, 8):
+                cfg = dict(symrate=symrate, oqpsk=oq, bps=bps, order=order, interp=interp)
+                o, r = oracle_mod.Oracle(**cfg), oracle_mod.Ref(kind="strict", **cfg)
+                assert np.array_equal(bits(o.taps()), bits(r.taps())), cfg
+                assert _same_run(o, r, raw) > 30_000, cfg
+
+
+def test_port_equals_reference_on_random_parameters(oracle_mod):
+    """Seeded fuzz over everything demod_init takes (demod.h:29): sample and symbol rates, order, oversampling,
+    PLL bandwidth, frequency limit, mode, sample format; ragged pushes on the port side."""
+    need_ref(oracle_mod)
+    from meteor_demod_b200 import synth
+    rng = np.random.default_rng(2024)
+    for trial in range(16):
+        oq = int(rng.integers(0, 2))
+        bps = int(rng.choice([8, 16, 32]))
+        symrate = int(rng.choice([72000, 80000, 64000]))
+        fs = int(rng.choice([230000, 250000, 1_000_000 // 4]))
+        cfg = dict(samplerate=fs, symrate=symrate, oqpsk=oq, bps=bps, order=int(rng.integers(4, 90)),
+                   interp=int(rng.integers(1, 9)), pll_bw=float(rng.choice([0.5, 1.0, 2.0, 4.0])),
+                   freq_max=float(rng.choice([-1.0, 0.05, 0.2, 0.6])))
+        raw = synth.make_raw(60_000, symrate=symrate, fs=fs, oqpsk=bool(oq), bps=bps, seed=100 + trial,
+                             cfo_hz=float(rng.uniform(-1500, 1500)))
+        o, r = oracle_mod.Oracle(**cfg), oracle_mod.Ref(kind="strict", **cfg)
+        w = r.process(raw)
+        cuts = np.sort(rng.integers(0, 60_000, 5))
+        parts, prev = [], 0
+        for c in list(cuts) + [60_000]:
+            parts.append(o.process(raw[2 * prev: 2 * int(c)]).soft)
+            prev = int(c)
+        got = np.concatenate(parts)
+        assert got.shape[0] == w.nsym and np.array_equal(got, w.soft), (trial, cfg)
+        assert np.array_equal(bits(o.history()), bits(r.history())), (trial, cfg)
