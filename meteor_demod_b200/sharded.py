@@ -182,7 +182,81 @@ def boundary_quadrants(soft, q, count, Bq, npairs=None, base=None):
     return k, same.float().mean(dim=1), cut
 
 
-def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None):
+def boundary_quadrants_oqpsk(soft, q, count, Bq, half, npairs=None):
+    """boundary_quadrants for OQPSK rows (torch ops; q absolute int64). The I arm is sampled half a symbol before
+    the Q arm (demod.c:66-83), and the four lock points of the loop are not alike: at an EVEN number of quarter
+    turns two rows take their symbols at the same instants and differ by a sign; at an ODD number the later
+    row's symbol instants sit half a symbol (`half` sub-steps) off, its Q arm carries the earlier row's I
+    stream and its I arm the earlier row's Q stream of the symbol before:
+        row b (k = 1):  b.Q_j = -a.I_{m+1},  b.I_j = a.Q_m      with  q_b[j] ~ q_a[m] + half
+    (k = 3: both signs flipped). The timing offset between paired symbols tells even from odd, a correlation
+    then picks the sign. Returns k, agreement, cut like boundary_quadrants."""
+    M = soft.shape[0]
+    dev = soft.device
+    if M < 2:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return z, torch.zeros(0, device=dev), z
+    B = Bq.to(torch.int64)
+    a_q, a_s, a_n = q[:-1], soft[:-1], count[:-1]
+    b_q, b_s, b_n = q[1:], soft[1:], count[1:]
+    ia = _first_at_or_after(a_q, a_n, B)
+    prev_q = torch.gather(a_q, 1, (ia - 1).clamp(min=0)[:, None]).squeeze(1)
+    next_q = torch.gather(a_q, 1, ia.clamp(max=a_q.shape[1] - 1)[:, None]).squeeze(1)
+    cut = torch.where((ia > 0) & (ia < a_n), (prev_q + next_q) // 2, B)
+    ib = _first_at_or_after(b_q, b_n, cut + 1)
+    navail = torch.minimum(a_n - ia - 1, b_n - ib).clamp(min=0)           # one symbol of row a in reserve (m + 1)
+    nmin = int(navail.min().item()) if (ia > 0).all() else 0
+    npairs = nmin if npairs is None else min(npairs, nmin)
+    if npairs < 8:
+        return torch.zeros(M - 1, dtype=torch.int64, device=dev), torch.zeros(M - 1, device=dev), cut
+    j = torch.arange(npairs, device=dev)
+    ga, gb = ia[:, None] + j[None, :], ib[:, None] + j[None, :]
+    d = (torch.gather(b_q, 1, gb) - torch.gather(a_q, 1, ga)).to(torch.float32)
+    dm = d.median(dim=1).values                                            # timing offset of row b against row a
+    odd = dm.abs() > half / 2
+    off = torch.where(dm > 0, 0, -1)                                       # m = ia + j + off for odd boundaries
+    gm = (ga + off[:, None]).clamp(min=0)
+
+    def col(t, idx, c):
+        return torch.gather(t[..., c], 1, idx).to(torch.float32)
+    aI, aQ = col(a_s, ga, 0), col(a_s, ga, 1)
+    bI, bQ = col(b_s, gb, 0), col(b_s, gb, 1)
+    aQm, aIm1 = col(a_s, gm, 1), col(a_s, gm + 1, 0)
+    even_score = (aI * bI + aQ * bQ).sum(1)                                # > 0: k = 0, < 0: k = 2
+    odd_score = (-aIm1 * bQ + aQm * bI).sum(1)                             # > 0: k = 1, < 0: k = 3
+    k = torch.where(odd, torch.where(odd_score >= 0, 1, 3), torch.where(even_score >= 0, 0, 2))
+    sg = torch.where((k == 0) | (k == 1), 1.0, -1.0)[:, None]
+    same_even = (torch.sign(sg * bI) == torch.sign(aI)) & (torch.sign(sg * bQ) == torch.sign(aQ)) & (d.abs() <= 2)
+    same_odd = (torch.sign(-sg * bQ) == torch.sign(aIm1)) & (torch.sign(sg * bI) == torch.sign(aQm)) & \
+               ((d - dm[:, None]).abs() <= 2)
+    same = torch.where(odd[:, None], same_odd, same_even)
+    return k, same.float().mean(dim=1), cut
+
+
+def turn_oqpsk_state(st, turns):
+    """A row's loop state moved from the lock point it acquired to the one `turns` quarter turns back (the
+    sequential run's), for OQPSK: the Costas NCO turns as for QPSK (p_phase -= turns*pi/2, pll.c:16); for an
+    odd count the arms also change roles -- what was sampled as I (at the pi crossing, timing.c:47-50) is the new
+    Q and vice versa -- so the timing NCO moves by pi, the dual-threshold state toggles, and the two remembered
+    samples swap with the signs of the turn: new Q' = +-old I, new I' = -+old Q (demod.c:54, timing.c:13).
+    st: dict of 1-D float64 tensors (p_phase, t_phase, t_dual_state, t_prev, oq_inphase); returns a new dict."""
+    kk = (turns & 3).to(torch.int64)
+    out = dict(st)
+    out["p_phase"] = (st["p_phase"].float().double() - kk.double() * 1.57079632679489661923).float().double()
+    odd = (kk & 1) == 1
+    s_q = torch.where(kk == 1, 1.0, -1.0).double()                        # new Q' = s_q * old I ; new I' = -s_q * old Q
+    flip = torch.where(kk == 2, -1.0, 1.0).double()                       # half a turn: both arms change sign
+    dual = st["t_dual_state"].to(torch.int64)
+    pi = 3.14159265358979323846
+    ph = st["t_phase"].float().double()
+    out["t_phase"] = torch.where(odd, torch.where(dual == 1, ph + pi, ph - pi), ph).float().double()
+    out["t_dual_state"] = torch.where(odd, 3 - dual, dual).double()
+    out["t_prev"] = torch.where(odd, s_q * st["oq_inphase"], flip * st["t_prev"])
+    out["oq_inphase"] = torch.where(odd, -s_q * st["t_prev"], flip * st["oq_inphase"])
+    return out
+
+
+def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half=None):
     """Quadrant scan + concatenation of the owned symbols.
 
     soft [M,cap,2] int8, q [M,cap] int64 ABSOLUTE sub-step index (sample*interp + sub-step from the
@@ -200,7 +274,13 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None):
     M, L, dev = soft.shape[0], plan.interp, soft.device
     big = torch.iinfo(torch.int64).max
     Bq = torch.tensor([plan.cut_target(first_chunk + c) for c in range(1, M)], dtype=torch.int64, device=dev)
-    k, agree, cut = boundary_quadrants(soft, q, count, Bq, base=base)
+    if oqpsk_half is not None:
+        if dist is not None and dist.get_world_size() > 1:
+            raise NotImplementedError("OQPSK time shards: single process only")
+        k, agree, cut = boundary_quadrants_oqpsk(soft, q if base is None else q.to(torch.int64) + base[:, None],
+                                                 count, Bq, oqpsk_half)
+    else:
+        k, agree, cut = boundary_quadrants(soft, q, count, Bq, base=base)
 
     k_prev, agree_prev, cut_prev = 0, None, None
     if world > 1:
@@ -311,6 +391,7 @@ class GpuEngine:
         plan.start(last chunk) + n_main + 2*overlap)."""
         from .demod import Demod
         self.plan, self.raw, self.first, self.raw_first = plan, raw, first_chunk, raw_first
+        self.oqpsk = bool(cfg.get("oqpsk"))
         self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
         self.d = Demod(nstreams=self.M, device=device, interp_factor=plan.interp, **cfg)
         n_all = plan.n_main + plan.overlap
@@ -404,11 +485,26 @@ class GpuEngine:
         self.d.import_states_device(buf, check=True)         # the import runs on the handle's own stream
         self.d.sync()
 
-    @staticmethod
-    def rotate_rows(rows, turns):
+    def rotate_rows(self, rows, turns):
         """Every row's Costas NCO turned back by `turns` quarter turns, exactly as lrpt_restore does:
-        p_phase = (float)((double)p_phase - (turns & 3) * M_PI/2)  (pll.c:16)."""
+        p_phase = (float)((double)p_phase - (turns & 3) * M_PI/2)  (pll.c:16). OQPSK rows (experimental on the
+        GPU, see ShardedDemod) also move their timing NCO and swap the remembered arm samples: turn_oqpsk_state."""
         from ._lib import State
+        if self.oqpsk:
+            out = rows.clone()
+            f32 = ("p_phase", "t_phase", "t_prev", "oq_inphase")
+            def field(name, dt):
+                o = getattr(State, name).offset
+                return out[:, o: o + 4].contiguous().view(dt).reshape(-1)
+            st = {k: field(k, torch.float32).double() for k in f32}
+            st["t_dual_state"] = field("t_dual_state", torch.int32).double()
+            new = turn_oqpsk_state(st, turns.to(out.device))
+            for k in f32:
+                o = getattr(State, k).offset
+                out[:, o: o + 4] = new[k].float().view(-1, 1).view(torch.uint8)
+            o = State.t_dual_state.offset
+            out[:, o: o + 4] = new["t_dual_state"].to(torch.int32).view(-1, 1).view(torch.uint8)
+            return out
         off = State.p_phase.offset
         out = rows.clone()
         ph = out[:, off: off + 4].contiguous().view(torch.float32).reshape(-1)
@@ -421,7 +517,7 @@ class GpuEngine:
         self.d.close()
 
 
-def run_handoff(eng, plan, first_chunk=0, dist=None):
+def run_handoff(eng, plan, first_chunk=0, dist=None, oqpsk_half=None):
     """Time-sharding with state hand-off between chunks (Tier-S, same cost as the two-pass scheme, longer
     effective warm-up): pass A = warm-up W from power-on; pass B = owned + overlap, giving the quadrant
     scan AND, at its end, the state of every row V samples past its successor's boundary; pass C = every
@@ -432,7 +528,11 @@ def run_handoff(eng, plan, first_chunk=0, dist=None):
     NCCL between GPUs); the quadrant scan's exchange is stitch()'s.
 
     eng: pass_a() -> head symbols of row 0, pass_b()/pass_c() -> (soft, q, count), export_rows() ->
-    [M, R] tensor, import_rows(rows), rotate_rows(rows, turns); eng.M local rows."""
+    [M, R] tensor, import_rows(rows), rotate_rows(rows, turns); eng.M local rows.
+    oqpsk_half: None for QPSK; for OQPSK the number of timing sub-steps in half a symbol (fs*interp/(2*symrate)):
+    the quadrant scan is then boundary_quadrants_oqpsk and the engine's rotate_rows must move a row turned by an
+    odd count as turn_oqpsk_state does. Checked with the CPU oracle as the engine (tests/test_sharded.py); the
+    GPU engine does not enable it yet."""
     import dataclasses
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
@@ -441,7 +541,7 @@ def run_handoff(eng, plan, first_chunk=0, dist=None):
         raise ValueError("the rank holding chunk 0 needs at least two chunks")
     head = eng.pass_a()
     soft_b, q_b, n_b, base_b = _rows4(eng.pass_b())
-    scan = stitch(soft_b, q_b, n_b, plan, first_chunk=first_chunk, dist=dist, base=base_b)
+    scan = stitch(soft_b, q_b, n_b, plan, first_chunk=first_chunk, dist=dist, base=base_b, oqpsk_half=oqpsk_half)
     K = chunk_turns(scan, M)
     row0 = soft_b[0, : int(n_b[0].item())].clone() if first_chunk == 0 else None   # pass C reuses the buffers
     turned = eng.rotate_rows(eng.export_rows(), K)
@@ -466,10 +566,10 @@ def run_handoff(eng, plan, first_chunk=0, dist=None):
         # rows 0 and 1 are one exact trajectory: the head, row 0's pass-B symbols, then row 1's pass-C symbols up
         # to its cut with row 2 -- i.e. the final table is rows 1.. with nothing cut off the front of row 1
         res = stitch(soft_c[1:], q_c[1:], n_c[1:], shifted, first_chunk=1, dist=dist,
-                     base=None if base_c is None else base_c[1:])
+                     base=None if base_c is None else base_c[1:], oqpsk_half=oqpsk_half)
         res["soft"] = torch.cat((_as_tensor(head, soft_c.device), row0, res["soft"]))
     else:
-        res = stitch(soft_c, q_c, n_c, shifted, first_chunk=first_chunk, dist=dist, base=base_c)
+        res = stitch(soft_c, q_c, n_c, shifted, first_chunk=first_chunk, dist=dist, base=base_c, oqpsk_half=oqpsk_half)
     res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
     return res
 
@@ -494,8 +594,14 @@ class ShardedDemod:
 
     def __init__(self, raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
                  interp_factor=5, two_pass=True, handoff=False, raw_first=0, **cfg):
+        self.oqpsk_half = None
         if cfg.get("oqpsk"):
-            raise NotImplementedError("time-sharding resolves the k*90 degree ambiguity of QPSK only")
+            # the OQPSK join and state turn (boundary_quadrants_oqpsk, turn_oqpsk_state) are checked with the CPU
+            # oracle as the engine; on the GPU engine they have not been run yet, hence the explicit opt-in
+            import os
+            if not (handoff and dist is None and os.environ.get("LRPT_EXPERIMENTAL_OQPSK_SHARDS")):
+                raise NotImplementedError("time-sharding on the GPU resolves the k*90 degree ambiguity of QPSK only")
+            self.oqpsk_half = cfg.get("samplerate", 230000) * interp_factor / (2.0 * cfg.get("symrate", 72000))
         self.plan = plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
         self.dist, self.two_pass, self.handoff = dist, two_pass, handoff
         world = dist.get_world_size() if dist is not None else 1
@@ -513,7 +619,7 @@ class ShardedDemod:
         eng, plan, c0, M = self.eng, self.plan, self.c0, self.c1 - self.c0
         l0 = eng.d.launch_count()
         if self.handoff:
-            res = run_handoff(eng, plan, first_chunk=c0, dist=self.dist)
+            res = run_handoff(eng, plan, first_chunk=c0, dist=self.dist, oqpsk_half=self.oqpsk_half)
         elif not self.two_pass:
             res = _stitch_rows(eng.run(), plan, first_chunk=c0, dist=self.dist)
         else:

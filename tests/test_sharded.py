@@ -286,13 +286,13 @@ class OracleEngine:
     """CPU stand-in for sharded.GpuEngine in run_handoff: one oracle per local chunk; a row of state is a
     float64 vector (every float32/int field exactly) followed by the delay line."""
 
-    def __init__(self, raw, plan, first_chunk=0, nchunks=None):
+    def __init__(self, raw, plan, first_chunk=0, nchunks=None, cfg=None):
         from oracle import pyoracle
-        self.plan, self.first = plan, first_chunk
+        self.plan, self.first, self.cfg = plan, first_chunk, dict(cfg or CFG)
         self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
         self.pad = np.zeros(2 * plan.padded, raw.dtype)
         self.pad[: raw.size] = raw
-        self.o = [pyoracle.Oracle(**CFG) for _ in range(self.M)]
+        self.o = [pyoracle.Oracle(**self.cfg) for _ in range(self.M)]
         self.keys = sorted(self.o[0].state())
 
     def _run(self, offset, n, want_q=True):
@@ -327,6 +327,13 @@ class OracleEngine:
 
     def rotate_rows(self, rows, turns):
         out = rows.clone()
+        if self.cfg.get("oqpsk"):
+            from meteor_demod_b200 import sharded
+            names = ("p_phase", "t_phase", "t_dual_state", "t_prev", "oq_inphase")
+            new = sharded.turn_oqpsk_state({k: out[:, self.keys.index(k)] for k in names}, turns)
+            for k in names:
+                out[:, self.keys.index(k)] = new[k]
+            return out
         j = self.keys.index("p_phase")
         ph = out[:, j].to(torch.float32)
         out[:, j] = (ph.double() - (turns & 3).double() * 1.57079632679489661923).float().double()
@@ -487,3 +494,29 @@ def test_stitch_kernels_equal_torch_ops_on_random_rows(lib):
         got = r0["soft"].cpu()
         nslots = (plan.nsamples * L - 1 - 3 + 1 + 13) // 14
         assert got.shape[0] == nslots, (trial, got.shape[0], nslots)
+
+
+def test_oqpsk_handoff_scheme_on_the_oracle(oracle_mod):
+    """OQPSK time shards, CPU oracle as the engine (the GPU engine does not enable them yet): the scan tells even
+    from odd quarter turns by the half-symbol timing offset and re-pairs the arms, the hand-off moves the timing
+    NCO along with the Costas NCO. Same symbol count as the sequential run, chunks 0 and 1 exact, every final
+    boundary aligned, eps at the QPSK level."""
+    from meteor_demod_b200 import sharded, synth
+    cfg = dict(symrate=80000, oqpsk=1, bps=8, order=32, interp=5)
+    n = 1_900_000
+    raw = synth.make_raw(n, symrate=80000, oqpsk=True, bps=8, cfo_hz=60.0, seed=31)
+    plan = sharded.Plan(n, CHUNK, WARM, OVERLAP, cfg["interp"])
+    half = 230000 * cfg["interp"] / (2 * 80000)
+    res = sharded.run_handoff(OracleEngine(raw, plan, cfg=cfg), plan, oqpsk_half=half)
+    seq = oracle_mod.Oracle(**cfg).process(raw, want_float=False).soft
+    got = res["soft"].numpy()
+    rep = tier_s_report(got, seq)
+    K = res["first_pass"]["K"].tolist()
+    assert any(k % 2 for k in K), K                               # the case that needs the re-pairing occurs
+    assert rep["n_stitched"] == rep["n_seq"]
+    assert res["k"].tolist() == [0] * (plan.nchunks - 2)
+    assert float(res["first_pass"]["agreement"].min()) > 0.99 and float(res["agreement"].min()) > 0.99
+    n01 = int(plan.boundary(2) * 80000 / 230000) - 16
+    assert np.array_equal(got[:n01], seq[:n01])
+    assert rep["frac_gt1"] < 0.01, rep
+    print("OQPSK hand-off Tier-S report:", rep, "first-pass K:", K)
