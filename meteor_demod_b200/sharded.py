@@ -275,8 +275,6 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half
     big = torch.iinfo(torch.int64).max
     Bq = torch.tensor([plan.cut_target(first_chunk + c) for c in range(1, M)], dtype=torch.int64, device=dev)
     if oqpsk_half is not None:
-        if dist is not None and dist.get_world_size() > 1:
-            raise NotImplementedError("OQPSK time shards: single process only")
         k, agree, cut = boundary_quadrants_oqpsk(soft, q if base is None else q.to(torch.int64) + base[:, None],
                                                  count, Bq, oqpsk_half)
     else:
@@ -313,8 +311,11 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half
             two_s[1, : soft.shape[1]] = soft[0]
             two_q[1, : soft.shape[1]] = _abs_row(q, base, 0)
             two_n = torch.stack((torch.tensor(n, dtype=torch.int64, device=dev), count[0]))
-            kp, ap, cp = boundary_quadrants(two_s, two_q, two_n,
-                                            torch.tensor([plan.cut_target(first_chunk)], device=dev))
+            tgt = torch.tensor([plan.cut_target(first_chunk)], device=dev)
+            if oqpsk_half is not None:
+                kp, ap, cp = boundary_quadrants_oqpsk(two_s, two_q, two_n, tgt, oqpsk_half)
+            else:
+                kp, ap, cp = boundary_quadrants(two_s, two_q, two_n, tgt)
             k_prev, agree_prev, cut_prev = int(kp[0].item()), float(ap[0].item()), int(cp[0].item())
 
     # (b) prefix sum of quarter turns over ranks

@@ -359,6 +359,45 @@ def test_handoff_scheme_on_the_oracle(stream):
     print("hand-off Tier-S report:", rep, "first-pass K:", res["first_pass"]["K"].tolist())
 
 
+OQ_CFG = dict(symrate=80000, oqpsk=1, bps=8, order=32, interp=5)
+OQ_HALF = 230000 * 5 / (2 * 80000)
+
+
+def make_oqpsk_stream():
+    from meteor_demod_b200 import synth
+    return synth.make_raw(1_900_000, symrate=80000, oqpsk=True, bps=8, cfo_hz=60.0, seed=31)
+
+
+def _oqpsk_rank_main(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from meteor_demod_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    raw = make_oqpsk_stream()
+    plan = sharded.Plan(raw.size // 2, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
+    c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
+    eng = OracleEngine(raw, plan, first_chunk=c0, nchunks=c1 - c0, cfg=OQ_CFG)
+    res = sharded.run_handoff(eng, plan, first_chunk=c0, dist=dist, oqpsk_half=OQ_HALF)
+    np.save(os.path.join(out_dir, "oq%d.npy" % rank), res["soft"].numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_oqpsk_handoff_equals_single_process(tmp_path):
+    """OQPSK shards over two ranks (gloo): boundary symbols, quarter turns and the predecessor state cross the
+    rank boundary; the concatenated output equals the single-process run."""
+    import torch.multiprocessing as mp
+    from meteor_demod_b200 import sharded
+    raw = make_oqpsk_stream()
+    plan = sharded.Plan(raw.size // 2, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
+    want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG), plan, oqpsk_half=OQ_HALF)["soft"].numpy()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_oqpsk_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.concatenate([np.load(tmp_path / ("oq%d.npy" % r)) for r in range(2)])
+    assert np.array_equal(got, want)
+
+
 def _handoff_rank_main(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
