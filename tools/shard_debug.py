@@ -1,3 +1,4 @@
+"""Scratch: which boundaries of a time-sharded run disagree, and what the two rows look like there."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,9 +11,10 @@ raw = synth.device_long_stream(per, N, total=plan.padded)
 sd = sharded.ShardedDemod(raw, N, chunk=C, warm=W, overlap=V, symrate=72000, bps=16, rrc_order=32, interp_factor=L)
 eng = sd.eng
 head = eng.warm_up()
-soft, q, count = eng.owned()
+soft, q, count, base = eng.owned()
 Bq = torch.tensor([plan.cut_target(c) for c in range(1, plan.nchunks)], dtype=torch.int64, device="cuda")
-k, agree, cut = sharded.boundary_quadrants(soft, q, count, Bq)
+k, agree, cut = sharded.boundary_quadrants(soft, q, count, Bq, base=base)
+q = q.to(torch.int64) + base[:, None]                      # absolute indices for the prints below
 bad = (agree < 0.9).nonzero().squeeze(1)
 print("pass B: nchunks", plan.nchunks, "bad boundaries", bad.tolist()[:20], "min agree", float(agree.min()))
 for b in bad.tolist()[:5]:
