@@ -16,7 +16,7 @@ raw = T.make_oqpsk_stream()
 n = raw.size // 2
 plan = sharded.Plan(n, T.CHUNK, T.WARM, T.OVERLAP, T.OQ_CFG["interp"])
 want = sharded.run_handoff(T.OracleEngine(raw, plan, cfg=T.OQ_CFG), plan, oqpsk_half=T.OQ_HALF)
-dev = torch.full((2 * plan.padded,), 128, dtype=torch.uint8, device="cuda")       # silence = offset-binary zero
+dev = torch.zeros(2 * plan.padded, dtype=torch.uint8, device="cuda")              # the padding the oracle engine uses
 dev[: raw.size] = torch.from_numpy(raw).cuda()
 got = sharded.demod_sharded(dev, n, chunk=T.CHUNK, warm=T.WARM, overlap=T.OVERLAP, symrate=80000, oqpsk=True, bps=8,
                             rrc_order=32, interp_factor=5, handoff=True)
