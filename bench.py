@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--single-pass", action="store_true")
     ap.add_argument("--handoff", action="store_true",
                     help="sharded: chunks continue from their predecessor's state (sharded.run_handoff; the default)")
+    ap.add_argument("--seed-carrier", action="store_true", help="sharded: chunks >= 1 start their Costas NCO at a coarse "
+                    "carrier estimate (meteor_demod_b200/acquire.py; opt-in, not what the reference does)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target CPU work per core for the baseline")
@@ -483,7 +485,7 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
     raw = synth.device_long_stream(period, N, total=span, bps=bps, sps=FS / symrate, first=s0)
     kw = dict(chunk=a.chunk, warm=a.warm, overlap=8192, device=local, dist=dist if world > 1 else None, raw_first=s0,
               symrate=symrate, bps=bps, rrc_order=order, interp_factor=interp, two_pass=not a.single_pass,
-              handoff=a.handoff)
+              handoff=a.handoff, seed_carrier=a.seed_carrier)
 
     def barrier():
         torch.cuda.synchronize()

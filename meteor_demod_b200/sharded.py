@@ -386,13 +386,16 @@ def chunk_turns(res, M):
 class GpuEngine:
     """Chunks of one device-resident raw stream through liblrpt_b200.so, one recurrence lane each."""
 
-    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, raw_first=0, **cfg):
+    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, raw_first=0, seed_carrier=False, **cfg):
         """raw: device tensor of the raw dtype whose item 0 is I of stream sample `raw_first` -- the whole
         (padded) stream, or just the span this engine's chunks read: [plan.start(first_chunk),
-        plan.start(last chunk) + n_main + 2*overlap)."""
+        plan.start(last chunk) + n_main + 2*overlap). seed_carrier (opt-in, not what the reference does; not
+        yet run on a GPU): every row but the stream's chunk 0 starts its Costas NCO at a coarse carrier estimate
+        (acquire.py), so the warm-up need not cover the reference's slow sweep at large offsets."""
         from .demod import Demod
         self.plan, self.raw, self.first, self.raw_first = plan, raw, first_chunk, raw_first
         self.oqpsk = bool(cfg.get("oqpsk"))
+        self.seed = bool(seed_carrier)
         self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
         self.d = Demod(nstreams=self.M, device=device, interp_factor=plan.interp, **cfg)
         n_all = plan.n_main + plan.overlap
@@ -429,6 +432,8 @@ class GpuEngine:
         Returns the warm-up symbols of local chunk 0 (they are output only if it is the stream's chunk 0)."""
         W = self.plan.warm
         self.d.reset()
+        if self.seed:
+            self.seed_carrier()
         if W:
             self.d.process_device(self._view(0, W), self.soft, nsym=self.nsym, nsamples=W)
         self.d.sync()
@@ -445,6 +450,24 @@ class GpuEngine:
         self.d.process_device(self._view(p.warm, n), self.soft, nsym=self.nsym, nsamples=n)
         self.d.sync()
         return self._result(p.warm)
+
+    def seed_carrier(self, nfft=1 << 17, group=1024):
+        """Rows of chunks >= 1: p_freq = the NCO step of a coarse carrier estimate over the row's first nfft samples
+        (everything else stays power-on). Chunk 0 is left alone: the head of the stream is the sequential run."""
+        from . import acquire
+        from ._lib import State
+        par = self.d.p
+        nfft = min(nfft, self.plan.n_main)
+        rows = self.export_rows()
+        off = State.p_freq.offset
+        for r0 in range(0, self.M, group):
+            r1 = min(self.M, r0 + group)
+            x = acquire.to_complex(self._view(0, nfft)[r0:r1], par.bps)
+            f = acquire.estimate_cfo(x, par.samplerate, par.symrate, bool(par.oqpsk))
+            pf = acquire.p_freq_for(f, par.symrate, bool(par.oqpsk))
+            first = 1 if self.first + r0 == 0 else 0
+            rows[r0 + first: r1, off: off + 4] = pf[first:].contiguous().view(-1, 1).view(torch.uint8)
+        self.import_rows(rows)
 
     # -- hand-off scheme (run_handoff) -----------------------------------------------------------------
     def pass_a(self):
@@ -594,7 +617,7 @@ class ShardedDemod:
     are built once; run() can be called repeatedly, e.g. by bench.py)."""
 
     def __init__(self, raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
-                 interp_factor=5, two_pass=True, handoff=False, raw_first=0, **cfg):
+                 interp_factor=5, two_pass=True, handoff=False, raw_first=0, seed_carrier=False, **cfg):
         self.oqpsk_half = None
         if cfg.get("oqpsk"):
             # the OQPSK join and state turn (boundary_quadrants_oqpsk, turn_oqpsk_state) are checked with the CPU
@@ -614,7 +637,7 @@ class ShardedDemod:
         if raw_first > plan.start(self.c0) or raw.numel() < need:
             raise ValueError("raw must hold samples [%d, %d) for chunks %d..%d" % (plan.start(self.c0), raw_first + need // 2, self.c0, self.c1 - 1))
         self.eng = GpuEngine(raw, plan, device=device, first_chunk=self.c0, nchunks=self.c1 - self.c0,
-                             raw_first=raw_first, **cfg)
+                             raw_first=raw_first, seed_carrier=seed_carrier, **cfg)
 
     def run(self):
         eng, plan, c0, M = self.eng, self.plan, self.c0, self.c1 - self.c0

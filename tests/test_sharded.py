@@ -286,9 +286,9 @@ class OracleEngine:
     """CPU stand-in for sharded.GpuEngine in run_handoff: one oracle per local chunk; a row of state is a
     float64 vector (every float32/int field exactly) followed by the delay line."""
 
-    def __init__(self, raw, plan, first_chunk=0, nchunks=None, cfg=None):
+    def __init__(self, raw, plan, first_chunk=0, nchunks=None, cfg=None, seed_carrier=False):
         from oracle import pyoracle
-        self.plan, self.first, self.cfg = plan, first_chunk, dict(cfg or CFG)
+        self.plan, self.first, self.cfg, self.seed = plan, first_chunk, dict(cfg or CFG), seed_carrier
         self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
         self.pad = np.zeros(2 * plan.padded, raw.dtype)
         self.pad[: raw.size] = raw
@@ -305,6 +305,16 @@ class OracleEngine:
         return outs
 
     def pass_a(self):
+        if self.seed:                                             # what GpuEngine.seed_carrier does, on CPU tensors
+            from meteor_demod_b200 import acquire
+            c, nfft = self.cfg, min(1 << 17, self.plan.n_main)
+            for i, o in enumerate(self.o):
+                if self.first + i == 0:
+                    continue                                      # chunk 0 stays the sequential run
+                s0 = self.plan.start(self.first + i)
+                x = acquire.to_complex(self.pad[2 * s0: 2 * (s0 + nfft)], c["bps"])
+                f = acquire.estimate_cfo(x, 230000, c["symrate"], bool(c["oqpsk"]))
+                o.set_state(p_freq=float(acquire.p_freq_for(float(f), c["symrate"], bool(c["oqpsk"]))))
         outs = self._run(0, self.plan.warm)
         return outs[0][0]
 
@@ -760,3 +770,41 @@ def test_oqpsk_handoff_scheme_on_the_oracle(oracle_mod):
     assert np.array_equal(got[:n01], seq[:n01])
     assert rep["frac_gt1"] < 0.01, rep
     print("OQPSK hand-off Tier-S report:", rep, "first-pass K:", K)
+
+
+def test_coarse_carrier_estimate():
+    """acquire.estimate_cfo: x^4 line for QPSK, the two x^2 lines at 2*f_c -+ symrate for OQPSK; rows in one call,
+    all three sample formats, offsets up to the reference's +-3.5 kHz sweep range."""
+    from meteor_demod_b200 import acquire, synth
+    for oq, symrate, bps in ((0, 72000, 16), (1, 80000, 8), (1, 72000, 32)):
+        cfos = (-3300.0, -900.0, 60.0, 1200.0, 2500.0)
+        rows = np.stack([synth.make_raw(1 << 17, symrate=symrate, oqpsk=bool(oq), bps=bps, cfo_hz=f, seed=3 + i)
+                         for i, f in enumerate(cfos)])
+        est = acquire.estimate_cfo(acquire.to_complex(rows, bps), 230000, symrate, bool(oq))
+        assert est.shape == (len(cfos),)
+        assert np.allclose(est.numpy(), cfos, atol=2.0), (oq, est.tolist())
+        one = acquire.estimate_cfo(acquire.to_complex(rows[1], bps), 230000, symrate, bool(oq))
+        assert abs(float(one) - cfos[1]) < 2.0
+    pf = acquire.p_freq_for(700.0, 72000, False)
+    assert abs(float(pf) * 72000 / (2 * np.pi) - 700.0) < 1e-3 and isinstance(pf, np.float32)
+
+
+def test_seeded_warm_up_on_the_oracle(oracle_mod):
+    """OQPSK at +1200 Hz: the reference's own loop needs ~850 k samples to pull the carrier in, so chunks that warm up
+    cold over 160 k samples are useless (the join reports it); with their Costas NCO seeded from the coarse estimate
+    the same plan gives the sequential run's symbol count, aligned boundaries and an eps at the usual level."""
+    from meteor_demod_b200 import sharded, synth
+    n = 2_600_000
+    raw = synth.make_raw(n, symrate=80000, oqpsk=True, bps=8, cfo_hz=1200.0, seed=4)
+    plan = sharded.Plan(n, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
+    seq = oracle_mod.Oracle(**OQ_CFG).process(raw, want_float=False).soft
+    cold = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG), plan, oqpsk_half=OQ_HALF)
+    assert float(cold["agreement"].min()) < 0.6                   # detected: chunks had not locked by their boundaries
+    res = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG, seed_carrier=True), plan, oqpsk_half=OQ_HALF)
+    rep = tier_s_report(res["soft"].numpy(), seq)
+    assert rep["n_stitched"] == rep["n_seq"]
+    assert res["k"].tolist() == [0] * (plan.nchunks - 2) and float(res["agreement"].min()) > 0.99
+    n01 = int(plan.boundary(2) * 80000 / 230000) - 16
+    assert np.array_equal(res["soft"].numpy()[:n01], seq[:n01])   # the head is still the sequential run
+    assert rep["frac_gt1"] < 0.01, rep
+    print("seeded OQPSK +1200 Hz:", rep)
