@@ -505,7 +505,8 @@ class GpuEngine:
         import ctypes as C
         sb = C.sizeof(State)
         buf = torch.cat((rows[:, :sb].reshape(-1), rows[:, sb:].reshape(-1))).contiguous()
-        torch.cuda.current_stream(buf.device).synchronize()  # the rows were produced on torch's stream (recv, cat);
+        if buf.is_cuda:
+            torch.cuda.current_stream(buf.device).synchronize()  # the rows were produced on torch's stream (recv, cat);
         self.d.import_states_device(buf, check=True)         # the import runs on the handle's own stream
         self.d.sync()
 

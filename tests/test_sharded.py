@@ -808,3 +808,139 @@ def test_seeded_warm_up_on_the_oracle(oracle_mod):
     assert np.array_equal(res["soft"].numpy()[:n01], seq[:n01])   # the head is still the sequential run
     assert rep["frac_gt1"] < 0.01, rep
     print("seeded OQPSK +1200 Hz:", rep)
+
+
+# ---------------------------------------------------------------- the GPU engine's Python layer, without a GPU --
+
+class OracleDemod:
+    """Stand-in for meteor_demod_b200.demod.Demod on CPU tensors, backed by one CPU oracle per stream, with the
+    byte layouts of the C ABI (lrpt_state_t + delay lines in one buffer, uint32 symbol indices): lets the tests run
+    sharded.GpuEngine / ShardedDemod themselves -- strided chunk views, per-row bases, state bytes turned or seeded in
+    place -- where no GPU exists. Test infrastructure only."""
+
+    def __init__(self, nstreams=1, device=0, interp_factor=5, symrate=72000, bps=16, rrc_order=32, oqpsk=False,
+                 samplerate=230000, **_):
+        from meteor_demod_b200 import make_params
+        from oracle import pyoracle
+        self.cfg = dict(samplerate=samplerate, symrate=symrate, oqpsk=int(bool(oqpsk)), bps=bps, order=rrc_order,
+                        interp=interp_factor)
+        self.p = make_params(samplerate=samplerate, symrate=symrate, interp_factor=interp_factor, rrc_order=rrc_order,
+                             oqpsk=oqpsk, bps=bps, nstreams=nstreams)
+        self.nstreams, self.bps, self.q, self.launches, self.snap = nstreams, bps, None, 0, None
+        self.new = lambda: pyoracle.Oracle(**self.cfg)
+        self.o = [self.new() for _ in range(nstreams)]
+
+    def capacity(self, n):
+        from meteor_demod_b200 import symbol_capacity
+        return symbol_capacity(n, self.p.samplerate, self.p.symrate)
+
+    def set_symbol_index_output(self, idx=None):
+        self.q = idx
+
+    def reset(self, stream=None, asynchronous=False):
+        self.o = [self.new() for _ in range(self.nstreams)]
+
+    def process_device(self, raw, soft, nsym=None, symf=None, stream=None, nsamples=None):
+        n = raw.shape[1] // 2 if nsamples is None else int(nsamples)
+        for r, o in enumerate(self.o):
+            w = o.process(raw[r, : 2 * n].contiguous().numpy(), want_float=False, want_substep=True)
+            soft[r, : 2 * w.nsym] = torch.from_numpy(w.soft.reshape(-1))
+            if self.q is not None:
+                self.q[r, : w.nsym] = torch.from_numpy(w.q.astype(np.int32))
+            if nsym is not None:
+                nsym[r] = w.nsym
+        self.launches += 1
+
+    def sync(self, stream=None):
+        pass
+
+    def launch_count(self):
+        return self.launches
+
+    def kernel_name(self):
+        return "oracle"
+
+    def _pack(self):
+        import ctypes as C
+        from meteor_demod_b200._lib import State
+        names = [f for f, _ in State._fields_ if f not in ("magic", "taps")]
+        blobs, hists = [], []
+        for o in self.o:
+            st, cur = State(), o.state()
+            st.magic, st.taps = 0x5350524C, o.s.taps
+            for k in names:
+                setattr(st, k, cur[k])
+            blobs.append(bytes(st))
+            hists.append(np.ascontiguousarray(o.history(), np.float32).tobytes())
+        return b"".join(blobs) + b"".join(hists)
+
+    def states_size(self):
+        return len(self._pack())
+
+    def export_states_device(self, buf):
+        buf.copy_(torch.frombuffer(bytearray(self._pack()), dtype=torch.uint8))
+
+    def import_states_device(self, buf, check=False):
+        import ctypes as C
+        from meteor_demod_b200._lib import State
+        raw = buf.numpy().tobytes()
+        sb = C.sizeof(State)
+        hb = (len(raw) - self.nstreams * sb) // self.nstreams
+        names = [f for f, _ in State._fields_ if f not in ("magic", "taps")]
+        for r, o in enumerate(self.o):
+            st = State.from_buffer_copy(raw[r * sb: (r + 1) * sb])
+            assert st.magic == 0x5350524C and st.taps == o.s.taps
+            o.set_state(**{k: getattr(st, k) for k in names})
+            off = self.nstreams * sb + r * hb
+            o.set_history(np.frombuffer(raw[off: off + hb], np.float32))
+
+    def snapshot(self):
+        self.snap = torch.frombuffer(bytearray(self._pack()), dtype=torch.uint8).clone()
+
+    def restore(self, quarter_turns=None):
+        self.import_states_device(self.snap)
+        if quarter_turns is not None:                     # lrpt_restore: p_phase = (float)((double)p_phase - k*pi/2)
+            for o, k in zip(self.o, quarter_turns):
+                o.s.p_phase = float(np.float32(np.float64(np.float32(o.s.p_phase)) - float(int(k) & 3) * 1.57079632679489661923))
+
+    def close(self):
+        pass
+
+
+def _engine_run(monkeypatch, raw, cfg, plan, **kw):
+    """sharded.ShardedDemod (GpuEngine inside) on CPU tensors with OracleDemod in place of the C ABI handle."""
+    from meteor_demod_b200 import demod, sharded
+    monkeypatch.setattr(demod, "Demod", OracleDemod)
+    t = torch.zeros(2 * plan.padded, dtype=torch.from_numpy(raw[:1]).dtype)
+    t[: raw.size] = torch.from_numpy(raw)
+    sd = sharded.ShardedDemod(t, raw.size // 2, chunk=plan.chunk, warm=plan.warm, overlap=plan.overlap, handoff=True,
+                              symrate=cfg["symrate"], bps=cfg["bps"], rrc_order=cfg["order"], interp_factor=cfg["interp"],
+                              oqpsk=bool(cfg["oqpsk"]), **kw)
+    try:
+        return sd.run()
+    finally:
+        sd.close()
+
+
+def test_gpu_engine_python_layer_on_cpu_stand_in(stream, monkeypatch):
+    """GpuEngine / ShardedDemod themselves (chunk views, bases, state bytes, hand-off) with a CPU stand-in for the
+    handle: byte-identical to run_handoff driven by the plain OracleEngine. QPSK (the path the GPU runs), then the
+    two opt-in paths that have not been on a GPU yet: OQPSK rows and the carrier-seeded warm-up."""
+    from meteor_demod_b200 import sharded
+    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
+    want = sharded.run_handoff(OracleEngine(stream, plan), plan)
+    got = _engine_run(monkeypatch, stream, CFG, plan)
+    assert got["launches"] == 3 and torch.equal(got["first_pass"]["K"], want["first_pass"]["K"])
+    assert np.array_equal(got["soft"].numpy(), want["soft"].numpy())
+
+    monkeypatch.setenv("LRPT_EXPERIMENTAL_OQPSK_SHARDS", "1")
+    raw = make_oqpsk_stream()
+    plan = sharded.Plan(raw.size // 2, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
+    want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG), plan, oqpsk_half=OQ_HALF)
+    got = _engine_run(monkeypatch, raw, OQ_CFG, plan)
+    assert any(k % 2 for k in got["first_pass"]["K"].tolist())
+    assert np.array_equal(got["soft"].numpy(), want["soft"].numpy())
+
+    want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG, seed_carrier=True), plan, oqpsk_half=OQ_HALF)
+    got = _engine_run(monkeypatch, raw, OQ_CFG, plan, seed_carrier=True)
+    assert np.array_equal(got["soft"].numpy(), want["soft"].numpy())
