@@ -25,6 +25,9 @@
 
 namespace lrpt {
 
+#ifndef LRPT_SPEC_PIPE
+#define LRPT_SPEC_PIPE 1          /* 1: symbol step split in two (demod_core.cuh), as in demod_ws.cu */
+#endif
 constexpr int SP_SLOTS  = 2;      /* candidate tile ring depth                       */
 constexpr int SP_NC     = 3;      /* candidate sub-steps per predicted event         */
 constexpr int SP_KMAX   = 12;     /* predicted events per stream and tile            */
@@ -137,6 +140,9 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 		const float2 *my_win = wins + (size_t)lane*wstride + 1;     /* +1: guard entry in front */
 		const float2 *my_cand = cand + (size_t)lane*SP_CSTR;
 		const int *my_ck = cks + (size_t)lane*SP_KSTR;
+#if LRPT_SPEC_PIPE
+		Osc osc; osc.s = fast_sin(-r.p_phase); osc.co = fast_cos(-r.p_phase); osc.bad = false;   /* pll.c:53-54 */
+#endif
 
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
@@ -152,6 +158,65 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 				int ckn = -0x40000000;
 				float2 c0 = make_float2(0.f, 0.f), c1 = c0, c2 = c0;
 				if (active) { ckn = tk[0]; c0 = tc[0]; c1 = tc[1]; c2 = tc[2]; }
+#if LRPT_SPEC_PIPE
+				/* symbol step split in two, the deferred half side by side with the next NCO search: see demod_ws.cu */
+				if (active && !have_x && Q < q1)
+					have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
+				while (true) {
+					__syncwarp();
+					const bool ready = active && have_x && Qx < q1;
+					if (!__any_sync(0xffffffffu, ready)) break;
+					if (ready) {
+						/* filter_get(flt, i) for sub-step Qx: from the candidates, or evaluated here */
+						while (ks < KM - 1 && ckn + 1 < Qx) {
+							ks++;
+							ckn = tk[ks]; c0 = tc[ks*NC]; c1 = tc[ks*NC + 1]; c2 = tc[ks*NC + 2];
+						}
+						const int d = Qx - ckn + 1;
+						float2 y;
+						const bool hit = d >= 0 && d < NC;
+						if (hit) y = (d == 0) ? c0 : (d == 1) ? c1 : c2;
+						else {
+							const int n = Qx/L, i = Qx - n*L;
+							y = fir_single<LP>(my_win + (t % NT)*T + (n - t*T), hT, taps, L - 1 - i);
+							misses++;
+						}
+						const int Qsym = Qx;
+						Pend pd;
+						step_critical<OQ>(r, c, half, y.x, y.y, osc.s, osc.co, pd);
+						/* publish the timing state the FIR warps extrapolate from */
+						pubs[lane] = make_float4(__int_as_float(Qsym), r.t_phase, r.t_freq, nco_threshold(r, c));
+						NcoTry tr = nco_try(r, c, a.nco_n0, Q, Qend);
+						if (hit) {                                       /* the next event will look at the next entry */
+							if (ks < KM - 1) {
+								ks++;
+								ckn = tk[ks]; c0 = tc[ks*NC]; c1 = tc[ks*NC + 1]; c2 = tc[ks*NC + 2];
+							} else ckn = -0x40000000;
+						}
+						const float s_gain = r.gain, s_pp = r.p_phase, s_pf = r.p_freq, s_pe = r.p_err;
+						const int s_lk = r.locked, s_lo = r.locked_once, s_ud = r.updown;
+						Osc next;
+						if (!step_deferred_fast<OQ>(r, c, lut, pd, next)) {   /* a shortcut was not provably exact */
+							r.gain = s_gain; r.p_phase = s_pp; r.p_freq = s_pf; r.p_err = s_pe;
+							r.locked = s_lk; r.locked_once = s_lo; r.updown = s_ud;
+							step_deferred_exact<OQ>(r, c, lut, pd, next);
+						}
+						osc = next;
+						if (!(OQ && pd.half == 1)) {
+							if (r.locked_once && first_lock < 0) first_lock = nsymbols;
+							if (off + nsym < a.cap) {
+								out[off + nsym] = make_char2((signed char)quantise(pd.ore), (signed char)quantise(pd.oim));
+								if (outf) outf[off + nsym] = make_float2(pd.ore, pd.oim);
+								if (outq) outq[off + nsym] = a.q_base + (uint32_t)Qsym;
+							}
+							nsym++; nsymbols++;
+						}
+						have_x = false;
+						if (Q < q1) have_x = nco_commit(r, c, tr, a.nco_n0, Q, q1, Qend, Qx, half);
+					}
+				}
+			}
+#else
 				while (true) {
 					if (active && !have_x && Q < q1)
 						have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
@@ -200,6 +265,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 					__syncwarp();
 				}
 			}
+#endif
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&empty[slot]);
 		}

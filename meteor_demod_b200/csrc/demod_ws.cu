@@ -25,6 +25,9 @@
 
 namespace lrpt {
 
+#ifndef LRPT_WS_PIPE
+#define LRPT_WS_PIPE 1             /* 1: symbol step split in two, deferred half side by side with the next NCO search */
+#endif
 constexpr int WS_T        = 32;    /* samples per tile = one FIR unit per stream  */
 constexpr int WS_SLOTS    = 2;     /* FIR tile ring depth                        */
 constexpr int WS_MAX_G    = 32;    /* streams per CTA = consumer lanes           */
@@ -150,6 +153,11 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		int Q = 0;                              /* sub-steps already taken               */
 		bool have_x = false; int Qx = 0, half = 0;
 		const float2 *my_tiles = tiles + (size_t)lane*S*T*L;
+#if LRPT_WS_PIPE
+		/* oscillator values the next mix will use (fast_sin/fast_cos(-p_phase), pll.c:53-54): known as soon
+		 * as the previous symbol step has written p_phase, so they are produced by THAT step's deferred half */
+		Osc osc; osc.s = fast_sin(-r.p_phase); osc.co = fast_cos(-r.p_phase); osc.bad = false;
+#endif
 
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
@@ -158,6 +166,49 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 				const int q0 = t*T*L;
 				const int q1 = min((t + 1)*T, a.nsamples)*L;
 				const float2 *tile = my_tiles + slot*T*L;
+#if LRPT_WS_PIPE
+				/* Symbol step split in two (demod_core.cuh, "split in two"). What the NEXT timing decision waits
+				 * for -- filter output -> bias/scale -> mix -> retime -> NCO search -> filter output -- is kept
+				 * short; the rest of the step (AGC magnitude and gain, Costas error, loop, lock detector, next
+				 * oscillator values, int8 store) sits in the same straight-line block as that search, so the
+				 * two dependency chains run side by side instead of one after the other. Same values, same
+				 * order per variable as demod.c:35-43 / :66-83. Rounds stay warp-uniform (lanes converged). */
+				if (active && !have_x && Q < q1)
+					have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
+				while (true) {
+					__syncwarp();
+					const bool ready = active && have_x && Qx < q1;
+					if (!__any_sync(0xffffffffu, ready)) break;
+					if (ready) {
+						const float2 y = tile[Qx - q0];              /* filter_get(flt, i) */
+						const int Qsym = Qx;
+						Pend pd;
+						step_critical<OQ>(r, c, half, y.x, y.y, osc.s, osc.co, pd);
+						/* timing-NCO search for the next symbol, tried ahead of the deferred half it overlaps with */
+						NcoTry tr = nco_try(r, c, a.nco_n0, Q, Qend);
+						const float s_gain = r.gain, s_pp = r.p_phase, s_pf = r.p_freq, s_pe = r.p_err;
+						const int s_lk = r.locked, s_lo = r.locked_once, s_ud = r.updown;
+						Osc next;
+						if (!step_deferred_fast<OQ>(r, c, lut, pd, next)) {   /* a shortcut was not provably exact */
+							r.gain = s_gain; r.p_phase = s_pp; r.p_freq = s_pf; r.p_err = s_pe;
+							r.locked = s_lk; r.locked_once = s_lo; r.updown = s_ud;
+							step_deferred_exact<OQ>(r, c, lut, pd, next);
+						}
+						osc = next;
+						if (!(OQ && pd.half == 1)) {
+							if (r.locked_once && first_lock < 0) first_lock = nsymbols;
+							if (off + nsym < a.cap) {
+								out[off + nsym] = make_char2((signed char)quantise(pd.ore), (signed char)quantise(pd.oim));
+								if (outf) outf[off + nsym] = make_float2(pd.ore, pd.oim);
+								if (outq) outq[off + nsym] = a.q_base + (uint32_t)Qsym;
+							}
+							nsym++; nsymbols++;
+						}
+						have_x = false;
+						if (Q < q1) have_x = nco_commit(r, c, tr, a.nco_n0, Q, q1, Qend, Qx, half);
+					}
+				}
+#else
 				/* Warp-uniform rounds, so that the lanes (streams) stay converged: in each round
 				 * every lane that still owes this tile a crossing runs its NCO search, then every
 				 * lane holding a crossing inside the tile takes its symbol step, all together. */
@@ -190,6 +241,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 					}
 					__syncwarp();
 				}
+#endif
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&empty[slot]);

@@ -97,10 +97,11 @@ static int reset_on(lrpt_demod *h, cudaStream_t st)
 static int upload_initial_state(lrpt_demod *h)
 {
 	std::vector<lrpt_state_t> init((size_t)h->p.nstreams, h->s0);
-	CU(h, cudaMemcpy(h->d_init, init.data(), sizeof(lrpt_state_t)*init.size(), cudaMemcpyHostToDevice));
+	/* on the handle's own (non-blocking) stream: a pageable cudaMemcpy on the legacy stream is not ordered with it */
+	CU(h, cudaMemcpyAsync(h->d_init, init.data(), sizeof(lrpt_state_t)*init.size(), cudaMemcpyHostToDevice, h->stream));
 	int rc = reset_on(h, h->stream);
 	if (rc) return rc;
-	CU(h, cudaStreamSynchronize(h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));                       /* init[] may go out of scope now */
 	memset(h->h_counts, 0, sizeof(uint32_t)*h->p.nstreams);
 	return LRPT_OK;
 }
@@ -151,7 +152,7 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 	CUC(cudaMemset(h->d_fallbacks, 0, sizeof(unsigned long long)));
 	CUC(cudaMallocHost(&h->h_counts, sizeof(uint32_t)*p->nstreams));
 	CUC(cudaMallocHost(&h->h_state, sizeof(lrpt_state_t)));
-	CUC(cudaMemcpy(h->d_taps, h->taps.data(), sizeof(float)*h->taps.size(), cudaMemcpyHostToDevice));
+	CUC(cudaMemcpyAsync(h->d_taps, h->taps.data(), sizeof(float)*h->taps.size(), cudaMemcpyHostToDevice, h->stream));   /* synchronised in upload_initial_state */
 #undef CUC
 	/* Kernel choice. Explicit requests must be supported by that kernel. AUTO goes by streams per SM:
 	 * few streams -> the warp-specialised kernels (shortest time per symbol of one stream: all-phase
@@ -518,11 +519,11 @@ extern "C" int lrpt_import_state(lrpt_demod_t *h, int stream, const void *buf, s
 				return fail(h, LRPT_ERR_STATE, "state blob: delay line holds a value no %d-bit input produces", h->p.bps);
 	}
 	CU(h, cudaSetDevice(h->p.device));
-	CU(h, cudaStreamSynchronize(h->stream));
-	CU(h, cudaMemcpy(h->d_states + stream, s, sizeof(*s), cudaMemcpyHostToDevice));
+	CU(h, cudaMemcpyAsync(h->d_states + stream, s, sizeof(*s), cudaMemcpyHostToDevice, h->stream));
 	if (h->H > 0)
-		CU(h, cudaMemcpy(h->d_hist + (size_t)stream*h->H, (const char *)buf + sizeof(lrpt_state_t),
-		                 sizeof(float2)*(size_t)h->H, cudaMemcpyHostToDevice));
+		CU(h, cudaMemcpyAsync(h->d_hist + (size_t)stream*h->H, (const char *)buf + sizeof(lrpt_state_t),
+		                      sizeof(float2)*(size_t)h->H, cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));                       /* the caller's buffer is free again */
 	return LRPT_OK;
 }
 
@@ -571,8 +572,11 @@ extern "C" int lrpt_snapshot(lrpt_demod_t *h)
 		CU(h, cudaMalloc(&h->d_snap, sizeof(lrpt_state_t)*ns));
 		CU(h, cudaMalloc(&h->d_snap_hist, sizeof(float2)*nh));
 	}
-	CU(h, cudaMemcpy(h->d_snap, h->d_states, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToDevice));
-	CU(h, cudaMemcpy(h->d_snap_hist, h->d_hist, sizeof(float2)*nh, cudaMemcpyDeviceToDevice));
+	/* device-to-device copies do not block the host and the legacy stream is not ordered with the handle's
+	 * non-blocking stream: issue them on that stream */
+	CU(h, cudaMemcpyAsync(h->d_snap, h->d_states, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToDevice, h->stream));
+	CU(h, cudaMemcpyAsync(h->d_snap_hist, h->d_hist, sizeof(float2)*nh, cudaMemcpyDeviceToDevice, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
 	return LRPT_OK;
 }
 
@@ -582,16 +586,19 @@ extern "C" int lrpt_restore(lrpt_demod_t *h, const int32_t *quarter_turns)
 	CU(h, cudaSetDevice(h->p.device));
 	CU(h, cudaDeviceSynchronize());
 	const size_t ns = (size_t)h->p.nstreams, nh = (size_t)(h->H > 0 ? h->H : 1)*ns;
-	CU(h, cudaMemcpy(h->d_hist, h->d_snap_hist, sizeof(float2)*nh, cudaMemcpyDeviceToDevice));
+	CU(h, cudaMemcpyAsync(h->d_hist, h->d_snap_hist, sizeof(float2)*nh, cudaMemcpyDeviceToDevice, h->stream));
 	if (!quarter_turns) {
-		CU(h, cudaMemcpy(h->d_states, h->d_snap, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToDevice));
+		CU(h, cudaMemcpyAsync(h->d_states, h->d_snap, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToDevice, h->stream));
+		CU(h, cudaStreamSynchronize(h->stream));
 		return LRPT_OK;
 	}
 	std::vector<lrpt_state_t> st(ns);
-	CU(h, cudaMemcpy(st.data(), h->d_snap, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToHost));
+	CU(h, cudaMemcpyAsync(st.data(), h->d_snap, sizeof(lrpt_state_t)*ns, cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
 	for (size_t s = 0; s < ns; s++)
 		st[s].p_phase = (float)((double)st[s].p_phase - (double)(quarter_turns[s] & 3)*1.57079632679489661923);
-	CU(h, cudaMemcpy(h->d_states, st.data(), sizeof(lrpt_state_t)*ns, cudaMemcpyHostToDevice));
+	CU(h, cudaMemcpyAsync(h->d_states, st.data(), sizeof(lrpt_state_t)*ns, cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
 	return LRPT_OK;
 }
 

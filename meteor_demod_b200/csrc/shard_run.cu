@@ -109,6 +109,9 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	const long long L = params->interp_factor;
 	const size_t M = nsamples > W ? (nsamples - W + C - 1)/C : 1;
 	if (M > (size_t)INT_MAX/2) return LRPT_ERR_ARG;
+	/* the rows' sub-step indices (sample*interp + sub-step, uint32 side output) must not wrap: the joins
+	 * rely on their ascending order */
+	if ((double)(W > C + V ? W : C + V)*(double)params->interp_factor >= 4294967296.0) return LRPT_ERR_ARG;
 	lrpt_shard_report_t r;
 	memset(&r, 0, sizeof(r));
 	r.nchunks = (int32_t)M; r.min_agreement_scan = r.min_agreement_final = 1.0f; r.first_lock_symbol = -1; r.aligned = 1;
@@ -151,6 +154,7 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 		                             d_nsym.as<uint32_t>(), nullptr, 0, nullptr));
 		RC(lrpt_sync(h, nullptr));
 		RC(lrpt_get_counts(h, counts.data(), (int)M));
+		for (size_t c = 0; c < M; c++) if (counts[c] > cap_row) return LRPT_ERR_CAP;   /* the stitch kernels trust the counts */
 		for (size_t c = 0; c < M; c++) base[c] = (long long)(c*C + first_sample)*L;
 		CK(cudaMemcpy(d_cnt.p, counts.data(), 4*M, cudaMemcpyHostToDevice));   /* uint32 counts < 2^31: read as int32 */
 		CK(cudaMemcpy(d_base.p, base.data(), 8*M, cudaMemcpyHostToDevice));
@@ -198,6 +202,8 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	}
 
 	ph.mark("quadrant scan + chunk 0");
+	const size_t out_head = out_n;                                  /* symbols of chunk 0's own trajectory (passes A + B) */
+	std::vector<long long> nsym_start(M, 0);                        /* symbol count row c inherits at the start of pass C */
 	/* hand-off: row c starts pass C from row c-1's end state, its Costas NCO turned back K[c-1] quarter turns
 	 * (p_phase = (float)((double)p_phase - K*pi/2), as lrpt_restore does; pll.c:16) */
 	{
@@ -217,7 +223,9 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 			sn[c] = sc[c - 1];
 			memcpy(nxt.data() + M*sb + c*hb, cur.data() + M*sb + (c - 1)*hb, hb);
 		}
+		for (size_t c = 0; c < M; c++) nsym_start[c] = sn[c].nsymbols;
 		CK(cudaMemcpy(d_states.p, nxt.data(), total, cudaMemcpyHostToDevice));
+		CK(cudaDeviceSynchronize());                                /* pageable upload on the legacy stream: not ordered with the handle's stream */
 		RC(lrpt_import_states_device(h, d_states.p, total, 1, nullptr));
 		RC(lrpt_sync(h, nullptr));
 	}
@@ -263,6 +271,27 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	CK(cudaMemcpy(dturn.p, turns.data(), 4*(size_t)n, cudaMemcpyHostToDevice));
 	RC(lrpt_shard_gather_device(soft1, soft_stride, n, longest, dst.as<int32_t>(), dln.as<int32_t>(), doff.as<int64_t>(),
 	                            dturn.as<int32_t>(), dout.as<int8_t>(), nullptr));
+	/* Stream-wide first lock (main.c:312 gates the output on pll_did_lock_once()). Chunk 0 may not have locked
+	 * by the end of its passes -- a recording that starts before the signal is up, the normal case for a
+	 * satellite pass -- so the answer is the first OUTPUT symbol that came from a loop which had locked once:
+	 * row c's pass C inherits its predecessor's flag and symbol count (exact for row 1, which continues chunk 0
+	 * bit for bit), so the row-local index at which it had locked is first_lock_symbol - inherited count. */
+	if (r.first_lock_symbol < 0) {
+		std::vector<int32_t> start(n);
+		CK(cudaMemcpy(start.data(), dst.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
+		const size_t tot_states = lrpt_states_size(h);
+		RC(lrpt_export_states_device(h, d_states.p, tot_states, nullptr));
+		RC(lrpt_sync(h, nullptr));
+		std::vector<lrpt_state_t> fin(M);
+		CK(cudaMemcpy(fin.data(), d_states.p, M*sizeof(lrpt_state_t), cudaMemcpyDeviceToHost));
+		for (int b = 0; b < n && r.first_lock_symbol < 0; b++) {
+			const lrpt_state_t &st = fin[(size_t)b + 1];
+			if (st.first_lock_symbol < 0 || len[b] <= 0) continue;
+			long long j = st.first_lock_symbol - nsym_start[(size_t)b + 1];     /* < 0: locked before this pass began */
+			if (j < start[b]) j = start[b];
+			if (j < (long long)start[b] + len[b]) r.first_lock_symbol = (long long)out_head + off[b] + (j - start[b]);
+		}
+	}
 	ph.mark("join (scan, ranges, gather)");
 	CK(cudaMemcpy(soft + 2*out_n, dout.p, 2*total, cudaMemcpyDeviceToHost));   /* default stream: ordered after the gather */
 	ph.mark("D2H of the symbols");

@@ -160,6 +160,54 @@ LRPT_DEV bool nco_to_crossing(Loop &r, const lrpt_consts_t &c, int n0, int &Q, i
 }
 
 /*
+ * nco_to_crossing in two parts, for callers that want the arithmetic of the search (a chain of dependent
+ * float adds) in the same straight-line block as other work: nco_try computes the windowed search from the
+ * CURRENT timing state without touching it, nco_commit accepts it under the same proof condition as above
+ * or runs the exhaustive chunks.
+ */
+struct NcoTry { float sel; int below; bool ok; };
+
+LRPT_DEV NcoTry nco_try(const Loop &r, const lrpt_consts_t &c, int n0, int Q, int Qend)
+{
+	const float f = r.t_freq;
+	const float thr = c.oqpsk ? __fmul_rn((float)r.t_dual, kPiF) : kTwoPiF;
+	float p = r.t_phase;
+	for (int b = 0; b < n0; b += 4) {                               /* n0 is warp-uniform and a multiple of 4 */
+		p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f); p = __fadd_rn(p, f);
+	}
+	float s[NCO_WINDOW];
+	float acc = p;
+	int below = 0;
+#pragma unroll
+	for (int j = 0; j < NCO_WINDOW; j++) {
+		acc = __fadd_rn(acc, f);
+		s[j] = acc;
+		below += (acc >= thr) ? 0 : 1;
+	}
+	float sel = s[NCO_WINDOW-1];
+#pragma unroll
+	for (int j = NCO_WINDOW - 2; j >= 0; j--) sel = (s[j] >= thr) ? s[j] : sel;
+	NcoTry t;
+	t.sel = sel; t.below = below;
+	t.ok = f > 0.0f && !(p >= thr) && below < NCO_WINDOW && Q + n0 + NCO_WINDOW <= Qend;
+	return t;
+}
+
+LRPT_DEV bool nco_commit(Loop &r, const lrpt_consts_t &c, const NcoTry &t, int n0, int &Q, int q1, int Qend,
+                         int &Qx, int &half)
+{
+	if (t.ok) {
+		r.t_phase = t.sel;
+		Qx = Q + n0 + t.below; Q = Qx + 1;
+		if (c.oqpsk) { half = r.t_dual; r.t_dual = (r.t_dual % 2) + 1; }
+		return true;
+	}
+	bool found = false;
+	while (!found && Q < q1) found = nco_chunk(r, c, Q, Qend, Qx, half);
+	return found;
+}
+
+/*
  * The same search with a 4-sum tested window behind n0 plain adds, n0 any warp-uniform count
  * (demod_lane.cu: n0 = nominal - 2, so the window is the four counts a locked loop produces).
  */

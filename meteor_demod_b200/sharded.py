@@ -369,9 +369,21 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half
 
 
 def split_chunks(nchunks, world, rank):
-    """Consecutive run of chunks of `rank`: [c0, c1)."""
-    per = math.ceil(nchunks / world)
-    return min(nchunks, rank * per), min(nchunks, (rank + 1) * per)
+    """Consecutive run of chunks of `rank`: [c0, c1). Even split: the first nchunks % world ranks take one
+    chunk more, so no rank is left without chunks when nchunks >= world."""
+    base, extra = divmod(nchunks, world)
+    c0 = rank * base + min(rank, extra)
+    return c0, c0 + base + (1 if rank < extra else 0)
+
+
+def check_layout(nchunks, world, handoff=False):
+    """The chunk layout of a multi-rank run, validated identically on every rank BEFORE any collective (a
+    one-sided exception would leave the other ranks blocked in recv / all_gather): every rank needs a chunk,
+    and in the hand-off scheme the rank holding chunk 0 needs two (chunk 1 continues chunk 0 exactly)."""
+    if nchunks < world:
+        raise ValueError("fewer chunks (%d) than ranks (%d)" % (nchunks, world))
+    if handoff and nchunks > 1 and split_chunks(nchunks, world, 0)[1] < 2:
+        raise ValueError("the rank holding chunk 0 needs at least two chunks (%d chunks over %d ranks)" % (nchunks, world))
 
 
 def chunk_turns(res, M):
@@ -389,8 +401,8 @@ class GpuEngine:
     def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, raw_first=0, seed_carrier=False, **cfg):
         """raw: device tensor of the raw dtype whose item 0 is I of stream sample `raw_first` -- the whole
         (padded) stream, or just the span this engine's chunks read: [plan.start(first_chunk),
-        plan.start(last chunk) + n_main + 2*overlap). seed_carrier (opt-in, not what the reference does; not
-        yet run on a GPU): every row but the stream's chunk 0 starts its Costas NCO at a coarse carrier estimate
+        plan.start(last chunk) + n_main + 2*overlap). seed_carrier (opt-in, not what the reference does): every
+        row but the stream's chunk 0 starts its Costas NCO at a coarse carrier estimate
         (acquire.py), so the warm-up need not cover the reference's slow sweep at large offsets."""
         from .demod import Demod
         self.plan, self.raw, self.first, self.raw_first = plan, raw, first_chunk, raw_first
@@ -512,8 +524,8 @@ class GpuEngine:
 
     def rotate_rows(self, rows, turns):
         """Every row's Costas NCO turned back by `turns` quarter turns, exactly as lrpt_restore does:
-        p_phase = (float)((double)p_phase - (turns & 3) * M_PI/2)  (pll.c:16). OQPSK rows (experimental on the
-        GPU, see ShardedDemod) also move their timing NCO and swap the remembered arm samples: turn_oqpsk_state."""
+        p_phase = (float)((double)p_phase - (turns & 3) * M_PI/2)  (pll.c:16). OQPSK rows also move their timing
+        NCO and swap the remembered arm samples: turn_oqpsk_state."""
         from ._lib import State
         if self.oqpsk:
             out = rows.clone()
@@ -557,7 +569,7 @@ def run_handoff(eng, plan, first_chunk=0, dist=None, oqpsk_half=None):
     oqpsk_half: None for QPSK; for OQPSK the number of timing sub-steps in half a symbol (fs*interp/(2*symrate)):
     the quadrant scan is then boundary_quadrants_oqpsk and the engine's rotate_rows must move a row turned by an
     odd count as turn_oqpsk_state does. Checked with the CPU oracle as the engine (tests/test_sharded.py); the
-    GPU engine does not enable it yet."""
+    GPU engine against that emulation byte for byte (test_gpu_oqpsk_handoff_equals_oracle_handoff)."""
     import dataclasses
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
@@ -621,18 +633,17 @@ class ShardedDemod:
                  interp_factor=5, two_pass=True, handoff=False, raw_first=0, seed_carrier=False, **cfg):
         self.oqpsk_half = None
         if cfg.get("oqpsk"):
-            # the OQPSK join and state turn (boundary_quadrants_oqpsk, turn_oqpsk_state) are checked with the CPU
-            # oracle as the engine; on the GPU engine they have not been run yet, hence the explicit opt-in
-            import os
-            if not (handoff and dist is None and os.environ.get("LRPT_EXPERIMENTAL_OQPSK_SHARDS")):
-                raise NotImplementedError("time-sharding on the GPU resolves the k*90 degree ambiguity of QPSK only")
+            # OQPSK: the join tells even from odd quarter turns by the half-symbol timing offset and the hand-off also
+            # moves the timing NCO (boundary_quadrants_oqpsk, turn_oqpsk_state). Only the hand-off scheme knows how;
+            # the two-pass scheme turns the Costas NCO alone, which is the QPSK ambiguity.
+            if not handoff:
+                raise NotImplementedError("OQPSK time shards need the hand-off scheme (handoff=True)")
             self.oqpsk_half = cfg.get("samplerate", 230000) * interp_factor / (2.0 * cfg.get("symrate", 72000))
         self.plan = plan = Plan(nsamples, chunk, warm, overlap, interp_factor)
         self.dist, self.two_pass, self.handoff = dist, two_pass, handoff
         world = dist.get_world_size() if dist is not None else 1
         rank = dist.get_rank() if dist is not None else 0
-        if plan.nchunks < world:
-            raise ValueError("fewer chunks (%d) than ranks (%d)" % (plan.nchunks, world))
+        check_layout(plan.nchunks, world, handoff)              # same verdict on every rank, before any collective
         self.c0, self.c1 = split_chunks(plan.nchunks, world, rank)
         need = (plan.start(self.c1 - 1) + plan.n_main + 2 * plan.overlap - raw_first) * 2
         if raw_first > plan.start(self.c0) or raw.numel() < need:

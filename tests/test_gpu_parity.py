@@ -366,3 +366,41 @@ def test_random_configurations(kernel, oracle_mod, lib):
             assert np.array_equal(got, w.soft), (case, cfg, ns, n, cut, s)
             assert_state_equal(d.state(s), o)
         d.close()
+
+
+C5_GRID = [(oq, order, L) for oq in (0, 1) for order in (16, 32, 64, 128) for L in (3, 5, 8)]
+
+
+@pytest.mark.parametrize("oq,order,L", C5_GRID, ids=["%s_o%d_L%d" % ("oqpsk80k_u8" if g[0] else "qpsk72k_s16", g[1], g[2]) for g in C5_GRID])
+def test_config5_whole_grid(oq, order, L, oracle_mod, lib):
+    """BASELINE config 5, every corner: RRC order {16,32,64,128} x oversampling {3,5,8} x {QPSK 72k s16, OQPSK 80k u8}.
+    33 streams through the lane kernel (stream 31 = last lane of a warp, stream 32 alone in the next warp) in two
+    ragged pushes, streams 0 / 31 / 32 bit for bit against the oracle (symbols, float symbols, complete state), and
+    stream 0 again through whatever kernel AUTO picks for a single stream."""
+    from meteor_demod_b200 import Demod, synth
+    symrate, bps = (80000, 8) if oq else (72000, 16)
+    cfg = dict(symrate=symrate, oqpsk=oq, bps=bps, order=order, interp=L)
+    n, cut = 36_000, 12_345
+    sig = [synth.make_raw(n, symrate=symrate, oqpsk=bool(oq), bps=bps, seed=700 + 3 * order + L + k, cfo_hz=-350.0 + 300.0 * k)
+           for k in range(3)]
+    raw = np.stack([sig[s % 3] if s < 31 else sig[s - 30] for s in range(33)])       # 31 -> sig[1], 32 -> sig[2]
+    d = demod_for(cfg, "lane", nstreams=33)
+    s1, c1, f1 = d.process_batch(np.ascontiguousarray(raw[:, : 2 * cut]), want_float=True)
+    s2, c2, f2 = d.process_batch(np.ascontiguousarray(raw[:, 2 * cut:]), want_float=True)
+    want = {}
+    for s in (0, 31, 32):
+        o = oracle_mod.Oracle(**cfg)
+        w = want[s] = o.process(raw[s])
+        got = np.concatenate([s1[s, : c1[s]], s2[s, : c2[s]]])
+        gotf = np.concatenate([f1[s, : c1[s]], f2[s, : c2[s]]])
+        assert got.shape[0] == w.nsym, s
+        assert np.array_equal(got, w.soft), s
+        assert np.array_equal(bits(gotf), bits(w.sym)), s
+        assert_state_equal(d.state(s), o)
+    d.close()
+    d1 = Demod(symrate=symrate, oqpsk=oq, bps=bps, rrc_order=order, interp_factor=L, kernel="auto")
+    assert d1.kernel_name() in ("ws", "spec")
+    soft, counts, symf = d1.process_batch(raw[:1], want_float=True)
+    w = want[0]
+    assert counts[0] == w.nsym and np.array_equal(soft[0, : w.nsym], w.soft) and np.array_equal(bits(symf[0, : w.nsym]), bits(w.sym))
+    d1.close()

@@ -128,6 +128,18 @@ def test_plan_geometry():
     assert p.boundary(p.nchunks - 1) < N <= WARM + p.nchunks * CHUNK
     assert p.padded >= N and p.start(3) == 3 * CHUNK
     assert [sharded.split_chunks(5, 2, r) for r in (0, 1)] == [(0, 3), (3, 5)]
+    # even split: no rank without chunks while nchunks >= world (5 over 4, 9 over 8), consecutive, complete
+    assert [sharded.split_chunks(5, 4, r) for r in range(4)] == [(0, 2), (2, 3), (3, 4), (4, 5)]
+    for n, w in ((9, 8), (8, 8), (32768, 8), (17, 3)):
+        runs = [sharded.split_chunks(n, w, r) for r in range(w)]
+        assert runs[0][0] == 0 and runs[-1][1] == n and all(a[1] == b[0] for a, b in zip(runs, runs[1:]))
+        assert min(b - a for a, b in runs) >= n // w >= 1
+    # layouts that cannot work are refused on EVERY rank alike, before any collective
+    with pytest.raises(ValueError):
+        sharded.check_layout(3, 4)
+    with pytest.raises(ValueError):
+        sharded.check_layout(4, 4, handoff=True)            # rank 0 would hold chunk 0 alone
+    sharded.check_layout(5, 4, handoff=True)
 
 
 def test_rotation_is_exact_group_action():
@@ -449,6 +461,57 @@ def test_gpu_handoff_equals_oracle_handoff(stream, lib):
     assert np.array_equal(out["soft"].cpu().numpy(), want["soft"].numpy())
 
 
+@pytest.mark.gpu
+def test_gpu_oqpsk_handoff_equals_oracle_handoff(lib, oracle_mod):
+    """OQPSK time shards on the GPU engine (odd quarter turns re-pair the arms and move the timing NCO) against the
+    same scheme driven by the CPU oracle as the engine: bit-exact engines, same join arithmetic, so byte-identical;
+    then Tier-S against the sequential run."""
+    from meteor_demod_b200 import sharded
+    raw = make_oqpsk_stream()
+    n = raw.size // 2
+    plan = sharded.Plan(n, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
+    want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG), plan, oqpsk_half=OQ_HALF)
+    dev = torch.zeros(2 * plan.padded, dtype=torch.uint8, device="cuda")
+    dev[: raw.size] = torch.from_numpy(raw).cuda()
+    got = sharded.demod_sharded(dev, n, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=80000, oqpsk=True, bps=8,
+                                rrc_order=32, interp_factor=5, handoff=True)
+    assert torch.equal(got["first_pass"]["K"].cpu(), want["first_pass"]["K"])
+    assert any(int(k) % 2 for k in want["first_pass"]["K"])       # the case that needs the re-pairing occurs
+    assert np.array_equal(got["soft"].cpu().numpy(), want["soft"].numpy())
+    seq = oracle_mod.Oracle(**OQ_CFG).process(raw, want_float=False).soft
+    rep = tier_s_report(got["soft"].cpu().numpy(), seq)
+    assert rep["n_stitched"] == rep["n_seq"] and rep["frac_gt1"] < 0.01, rep
+    with pytest.raises(NotImplementedError):
+        sharded.demod_sharded(dev, n, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=80000, oqpsk=True, bps=8,
+                              rrc_order=32, interp_factor=5, handoff=False)
+
+
+@pytest.mark.gpu
+def test_gpu_seeded_warm_up(lib, oracle_mod):
+    """seed_carrier on the GPU engine: OQPSK at +1200 Hz, where cold chunks cannot lock within the warm-up. The coarse
+    estimate is an FFT in float32 (on the GPU here, on the CPU in the oracle-driven test), so the seed may differ in
+    the last bit and the comparison is against the SEQUENTIAL run: same symbol count, aligned boundaries, head exact,
+    eps at the usual level."""
+    from meteor_demod_b200 import sharded, synth
+    n = 2_600_000
+    raw = synth.make_raw(n, symrate=80000, oqpsk=True, bps=8, cfo_hz=1200.0, seed=4)
+    plan = sharded.Plan(n, CHUNK, WARM, OVERLAP, 5)
+    dev = torch.zeros(2 * plan.padded, dtype=torch.uint8, device="cuda")
+    dev[: raw.size] = torch.from_numpy(raw).cuda()
+    kw = dict(chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=80000, oqpsk=True, bps=8, rrc_order=32, interp_factor=5, handoff=True)
+    cold = sharded.demod_sharded(dev, n, **kw)
+    assert float(cold["agreement"].min()) < 0.6                   # detected: chunks had not locked by their boundaries
+    got = sharded.demod_sharded(dev, n, seed_carrier=True, **kw)
+    seq = oracle_mod.Oracle(**OQ_CFG).process(raw, want_float=False).soft
+    a = got["soft"].cpu().numpy()
+    rep = tier_s_report(a, seq)
+    assert rep["n_stitched"] == rep["n_seq"], rep
+    assert got["k"].tolist() == [0] * (plan.nchunks - 2) and float(got["agreement"].min()) > 0.99
+    n01 = int(plan.boundary(2) * 80000 / 230000) - 16
+    assert np.array_equal(a[:n01], seq[:n01])
+    assert rep["frac_gt1"] < 0.01, rep
+
+
 def test_long_stream_windows_are_consistent():
     """Every rank generates only its time slice of the synthetic stream (bench.py --mode sharded): a window
     must hold exactly the samples the whole stream holds there, zero padding beyond the end included."""
@@ -572,178 +635,6 @@ def test_stitch_kernels_equal_torch_ops_on_random_rows(lib):
 
 OQ_CFG = dict(symrate=80000, oqpsk=1, bps=8, order=32, interp=5)
 OQ_HALF = 230000 * 5 / (2 * 80000)
-
-
-def make_oqpsk_stream():
-    from meteor_demod_b200 import synth
-    return synth.make_raw(1_900_000, symrate=80000, oqpsk=True, bps=8, cfo_hz=60.0, seed=31)
-
-
-def _oqpsk_rank_main(rank, world, port, out_dir):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch.distributed as dist
-    from meteor_demod_b200 import sharded
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    raw = make_oqpsk_stream()
-    plan = sharded.Plan(raw.size // 2, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
-    c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
-    eng = OracleEngine(raw, plan, first_chunk=c0, nchunks=c1 - c0, cfg=OQ_CFG)
-    res = sharded.run_handoff(eng, plan, first_chunk=c0, dist=dist, oqpsk_half=OQ_HALF)
-    np.save(os.path.join(out_dir, "oq%d.npy" % rank), res["soft"].numpy())
-    dist.destroy_process_group()
-
-
-def test_two_rank_gloo_oqpsk_handoff_equals_single_process(tmp_path):
-    """OQPSK shards over two ranks (gloo): boundary symbols, quarter turns and the predecessor state cross the
-    rank boundary; the concatenated output equals the single-process run."""
-    import torch.multiprocessing as mp
-    from meteor_demod_b200 import sharded
-    raw = make_oqpsk_stream()
-    plan = sharded.Plan(raw.size // 2, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
-    want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG), plan, oqpsk_half=OQ_HALF)["soft"].numpy()
-    port = 31500 + os.getpid() % 2000
-    mp.spawn(_oqpsk_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    got = np.concatenate([np.load(tmp_path / ("oq%d.npy" % r)) for r in range(2)])
-    assert np.array_equal(got, want)
-
-
-def _handoff_rank_main(rank, world, port, out_dir):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch.distributed as dist
-    from meteor_demod_b200 import sharded
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    raw = make_stream()
-    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
-    c0, c1 = sharded.split_chunks(plan.nchunks, world, rank)
-    res = sharded.run_handoff(OracleEngine(raw, plan, c0, c1 - c0), plan, first_chunk=c0, dist=dist)
-    np.save(os.path.join(out_dir, "hpart%d.npy" % rank), res["soft"].numpy())
-    dist.destroy_process_group()
-
-
-def test_two_rank_gloo_handoff_equals_single_process(stream, tmp_path):
-    """The hand-off scheme over 2 ranks (gloo): the predecessor state of rank 1's first chunk travels by
-    send/recv; the concatenated output equals the single-process run."""
-    import torch.multiprocessing as mp
-    from meteor_demod_b200 import sharded
-    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
-    want = sharded.run_handoff(OracleEngine(stream, plan), plan)["soft"].numpy()
-    port = 33500 + os.getpid() % 2000
-    mp.spawn(_handoff_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    got = np.concatenate([np.load(tmp_path / ("hpart%d.npy" % r)) for r in range(2)])
-    assert np.array_equal(got, want)
-
-
-@pytest.mark.gpu
-def test_gpu_handoff_equals_oracle_handoff(stream, lib):
-    from meteor_demod_b200 import sharded
-    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
-    want = sharded.run_handoff(OracleEngine(stream, plan), plan)
-    raw = torch.zeros(2 * plan.padded, dtype=torch.int16, device="cuda")
-    raw[: stream.size] = torch.from_numpy(stream).cuda()
-    out = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
-                                rrc_order=32, interp_factor=5, handoff=True)
-    assert torch.equal(out["first_pass"]["K"].cpu(), want["first_pass"]["K"])
-    assert np.array_equal(out["soft"].cpu().numpy(), want["soft"].numpy())
-
-
-def test_long_stream_windows_are_consistent():
-    """Every rank generates only its time slice of the synthetic stream (bench.py --mode sharded): a window
-    must hold exactly the samples the whole stream holds there, zero padding beyond the end included."""
-    from meteor_demod_b200 import synth
-    per = synth.baseband(23000, periodic=True, seed=3).astype(np.complex64)
-    n = 20_000
-    full = synth.device_long_stream(per, n, total=n + 3000, device="cpu", block=4096)
-    assert full.numel() == 2 * (n + 3000) and not full[2 * n:].any() and full[: 2 * n].any()
-    for first, total in ((0, 5000), (4096, 4096), (5000, 9000), (12_345, 10_655), (19_999, 50), (20_000, 10)):
-        win = synth.device_long_stream(per, n, total=total, device="cpu", block=4096, first=first)
-        assert torch.equal(win, full[2 * first: 2 * (first + total)]), (first, total)
-
-
-@pytest.mark.gpu
-def test_single_call_c_entry_point_equals_python_handoff(stream, lib):
-    """lrpt_sharded_process (host buffer in, stitched symbols out, no Python in the loop) against the torch-
-    orchestrated hand-off run on the same plan: same kernels, same arithmetic, so byte-identical; plus its
-    report, the one-chunk case (exact) and argument checks."""
-    from meteor_demod_b200 import LrptError, sharded
-    from oracle import pyoracle
-    plan = sharded.Plan(N, CHUNK, WARM, OVERLAP, CFG["interp"])
-    raw = torch.zeros(2 * plan.padded, dtype=torch.int16, device="cuda")
-    raw[: stream.size] = torch.from_numpy(stream).cuda()
-    want = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
-                                 rrc_order=32, interp_factor=5, handoff=True)
-    got, rep = sharded.process_host(stream, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16,
-                                    rrc_order=32, interp_factor=5)
-    assert np.array_equal(got, want["soft"].cpu().numpy())
-    assert rep["nchunks"] == plan.nchunks and rep["launches"] == 3 and rep["aligned"] == 1
-    assert abs(rep["min_agreement_final"] - float(want["agreement"].min())) < 1e-6
-    assert abs(rep["min_agreement_scan"] - float(want["first_pass"]["agreement"].min())) < 1e-6
-    seq = pyoracle.Oracle(**CFG).process(stream, want_float=False)
-    assert rep["first_lock_symbol"] == (int(np.argmax(seq.lock_once)) if seq.lock_once.any() else -1)
-    # a recording shorter than warm-up + one chunk is one chunk: the sequential run itself
-    short = stream[: 2 * 300_000]
-    got1, rep1 = sharded.process_host(short, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
-    w1 = pyoracle.Oracle(**CFG).process(short, want_float=False)
-    assert rep1["nchunks"] == 1 and np.array_equal(got1, w1.soft)
-    # a stream that ends inside chunk 1's overlap: nothing from the zero padding
-    n2 = WARM + CHUNK + 5000
-    got2, rep2 = sharded.process_host(stream[: 2 * n2], chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
-    w2 = pyoracle.Oracle(**CFG).process(stream[: 2 * n2], want_float=False)
-    assert rep2["nchunks"] == 2 and np.array_equal(got2, w2.soft)          # chunks 0 and 1 are exact
-    with pytest.raises(LrptError):
-        sharded.process_host(stream, chunk=CHUNK + 4, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
-    with pytest.raises(LrptError):
-        sharded.process_host(stream, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16, oqpsk=True)
-
-
-@pytest.mark.gpu
-def test_stitch_kernels_equal_torch_ops_on_random_rows(lib):
-    """csrc/shard_stitch.cu against the torch formulation of the same join (boundary_quadrants / stitch with
-    absolute int64 indices) on random rows: ragged counts, random quarter turns per row, timing jitter, stale
-    entries behind the valid part, boundaries with few pairs."""
-    from meteor_demod_b200 import sharded
-    g = torch.Generator().manual_seed(5)
-    for trial, (M, C, V, L) in enumerate(((9, 4000, 512, 5), (3, 900, 96, 8), (40, 2500, 256, 3), (2, 700, 64, 5))):
-        plan = sharded.Plan(M * C + 300, C, 300, V, L)
-        M = plan.nchunks
-        n_row = plan.n_main + V
-        cap = n_row * L // 14 + 40
-        truth = torch.randint(0, 4, (plan.padded * L // 14 + 8,), generator=g)      # the stream's symbols (quadrant per slot)
-        soft = torch.zeros((M, cap, 2), dtype=torch.int8)
-        q = torch.randint(0, 1 << 20, (M, cap), generator=g).to(torch.int32)          # stale garbage everywhere first
-        count = torch.zeros(M, dtype=torch.int64)
-        base = torch.tensor([plan.start(c) * L for c in range(M)], dtype=torch.int64)
-        turn = torch.randint(0, 4, (M,), generator=g)
-        for c in range(M):
-            slots = torch.arange((plan.start(c) * L + 13) // 14, (plan.start(c) + n_row) * L // 14)
-            slots = slots[: cap - int(torch.randint(0, 30, (1,), generator=g))]
-            n = slots.numel()
-            jit = torch.randint(-1, 2, (n,), generator=g)
-            q[c, :n] = (slots * 14 + 3 + jit - base[c]).clamp(min=0).to(torch.int32)
-            amp = torch.randint(20, 120, (n, 2), generator=g)
-            sgn = torch.tensor([[1, 1], [-1, 1], [-1, -1], [1, -1]])[truth[slots]]
-            noise = (torch.rand(n, 2, generator=g) < 0.03).long() * -2 + 1           # a few wrong hard decisions
-            s = (amp * sgn * noise).to(torch.int8)
-            soft[c, :n] = sharded.rotate_quarter_turns(s, int(-turn[c]) % 4)
-            count[c] = n
-        dsoft, dq, dcount, dbase = soft.cuda(), q.cuda(), count.cuda(), base.cuda()
-        q_abs = dq.to(torch.int64) + dbase[:, None]
-        Bq = torch.tensor([plan.cut_target(c) for c in range(1, M)], dtype=torch.int64, device="cuda")
-        k1, a1, c1 = sharded.boundary_quadrants(dsoft, dq, dcount, Bq, base=dbase)    # kernels
-        k0, a0, c0 = sharded.boundary_quadrants(dsoft, q_abs, dcount, Bq)              # torch ops
-        assert torch.equal(k1, k0) and torch.equal(c1, c0) and torch.allclose(a1, a0, atol=1e-6), trial
-        want_k = (turn[1:] - turn[:-1]) % 4
-        assert torch.equal(k0.cpu(), want_k), trial
-        r1 = sharded.stitch(dsoft, dq, dcount, plan, base=dbase)
-        r0 = sharded.stitch(dsoft, q_abs, dcount, plan)
-        assert torch.equal(r1["soft"], r0["soft"]) and r1["K_last"] == r0["K_last"], trial
-        # every slot of the stream exactly once, in order, turned back to row 0's lock point
-        got = r0["soft"].cpu()
-        nslots = (plan.nsamples * L - 1 - 3 + 1 + 13) // 14
-        assert got.shape[0] == nslots, (trial, got.shape[0], nslots)
 
 
 def test_oqpsk_handoff_scheme_on_the_oracle(oracle_mod):
@@ -933,7 +824,6 @@ def test_gpu_engine_python_layer_on_cpu_stand_in(stream, monkeypatch):
     assert got["launches"] == 3 and torch.equal(got["first_pass"]["K"], want["first_pass"]["K"])
     assert np.array_equal(got["soft"].numpy(), want["soft"].numpy())
 
-    monkeypatch.setenv("LRPT_EXPERIMENTAL_OQPSK_SHARDS", "1")
     raw = make_oqpsk_stream()
     plan = sharded.Plan(raw.size // 2, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
     want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG), plan, oqpsk_half=OQ_HALF)
