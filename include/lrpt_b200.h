@@ -234,6 +234,20 @@ typedef struct lrpt_shard_report {
 int  lrpt_sharded_process(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
                           int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep);
 
+/* ---- the feed-forward stage alone (csrc/fir_stage.cu) ----------------------------------------------
+ * filter_fwd_sample + filter_get (filter.c:39-65) for EVERY (sample n, timing sub-step i) of `nrows` rows,
+ * device buffers: d_out[row][n*L + i] = the complex value filter_get(flt, i) returns after sample n of the
+ * row has been pushed (float2: re, im), starting from the zeroed delay line of filter_init_rrc (filter.c:16).
+ * The reference evaluates this lazily, once per symbol (demod.c:35); the product kernels do too. This entry
+ * point materialises the whole stage so that it can be measured against its own roofline (2*bps/8 bytes in,
+ * 8*L bytes out and 4*taps*L flops per sample) and compared value by value with filter_get.
+ * mode 0: multiply and add rounded separately, oldest tap first -- bit-identical to filter_get;
+ * mode 1: fused multiply-add (one rounding per tap; statistical parity only).
+ * Strides in bytes, pointers and strides 16-byte aligned, interp_factor <= 8, taps <= 257; asynchronous on
+ * `cuda_stream` except for a short synchronisation while the tap table is uploaded. */
+int  lrpt_fir_stage_device(const lrpt_params_t *p, const void *d_raw, size_t raw_stride, int nrows, size_t nsamples,
+                           float *d_out, size_t out_stride, int mode, void *cuda_stream);
+
 /* ---- introspection -------------------------------------------------------------- */
 /*
  * Host-only (needs no CUDA device): what lrpt_create derives from `p`, exactly as

@@ -256,6 +256,21 @@ def turn_oqpsk_state(st, turns):
     return out
 
 
+def _neighbour_exchange(dist, to_next, from_prev):
+    """One batched point-to-point exchange down the chain of ranks: `to_next` (tensor or None) goes to rank + 1,
+    `from_prev` (tensor or None) is filled by rank - 1. With NCCL the pair is one grouped launch
+    (batch_isend_irecv = ncclGroupStart/End) instead of separate, serialised sends and receives."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops = []
+    if to_next is not None and rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, to_next, rank + 1))
+    if from_prev is not None and rank > 0:
+        ops.append(dist.P2POp(dist.irecv, from_prev, rank - 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half=None):
     """Quadrant scan + concatenation of the owned symbols.
 
@@ -284,8 +299,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half
     if world > 1:
         # (a) hand the neighbourhood of my last chunk's far boundary to the next rank
         width = int(plan.overlap) + 64
-        pack = torch.zeros((width, 3), dtype=torch.int64, device=dev)
-        npack = torch.zeros(1, dtype=torch.int64, device=dev)
+        pack = torch.zeros((width + 1, 3), dtype=torch.int64, device=dev)     # row `width` carries the fill count
         if first_chunk + M < plan.nchunks:
             nextB = plan.cut_target(first_chunk + M)
             n = int(count[-1].item())
@@ -293,14 +307,10 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half
             sel = (q_last[:n] >= nextB - 64 * L).nonzero().squeeze(1)[:width]
             pack[: sel.numel(), 0] = q_last[sel]
             pack[: sel.numel(), 1:] = soft[-1, sel].to(torch.int64)
-            npack[0] = sel.numel()
-        recv, nrecv = torch.zeros_like(pack), torch.zeros_like(npack)
-        reqs = [dist.isend(pack, rank + 1), dist.isend(npack, rank + 1)] if rank + 1 < world else []
-        if rank > 0:
-            dist.recv(recv, rank - 1)
-            dist.recv(nrecv, rank - 1)
-        for r_ in reqs:
-            r_.wait()
+            pack[width, 0] = sel.numel()
+        recv = torch.zeros_like(pack)
+        _neighbour_exchange(dist, pack, recv)
+        nrecv = recv[width, 0]
         if rank > 0:
             n = int(nrecv.item())
             cap2 = max(n, soft.shape[1])
@@ -554,7 +564,26 @@ class GpuEngine:
         self.d.close()
 
 
-def run_handoff(eng, plan, first_chunk=0, dist=None, oqpsk_half=None):
+class _Phases:
+    """Wall time of the phases of one run (every phase ends in a device synchronisation of its own, so the host
+    clock brackets the device work). Disabled unless a dict is passed in."""
+
+    def __init__(self, out):
+        import time
+        self.out, self.clock = out, time.perf_counter
+        self.t = self.clock()
+
+    def mark(self, name):
+        if self.out is None:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        now = self.clock()
+        self.out[name] = self.out.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
+def run_handoff(eng, plan, first_chunk=0, dist=None, oqpsk_half=None, phase_ms=None):
     """Time-sharding with state hand-off between chunks (Tier-S, same cost as the two-pass scheme, longer
     effective warm-up): pass A = warm-up W from power-on; pass B = owned + overlap, giving the quadrant
     scan AND, at its end, the state of every row V samples past its successor's boundary; pass C = every
@@ -576,28 +605,29 @@ def run_handoff(eng, plan, first_chunk=0, dist=None, oqpsk_half=None):
     M = eng.M
     if first_chunk == 0 and M < 2 and plan.nchunks > 1:
         raise ValueError("the rank holding chunk 0 needs at least two chunks")
+    ph = _Phases(phase_ms)
     head = eng.pass_a()
+    ph.mark("pass_a_warm_up")
     soft_b, q_b, n_b, base_b = _rows4(eng.pass_b())
+    ph.mark("pass_b_owned")
     scan = stitch(soft_b, q_b, n_b, plan, first_chunk=first_chunk, dist=dist, base=base_b, oqpsk_half=oqpsk_half)
+    ph.mark("quadrant_scan")
     K = chunk_turns(scan, M)
     row0 = soft_b[0, : int(n_b[0].item())].clone() if first_chunk == 0 else None   # pass C reuses the buffers
     turned = eng.rotate_rows(eng.export_rows(), K)
     incoming = turned[:1].clone()                                   # placeholder for the row that has no predecessor
-    req = None
     if world > 1:
-        if rank + 1 < world and first_chunk + M < plan.nchunks:
-            req = dist.isend(turned[-1:].contiguous(), rank + 1)
-        if rank > 0:
-            dist.recv(incoming, rank - 1)
-        if req is not None:
-            req.wait()
+        # "boundary state handed rank to rank": one state (lrpt_state_t + delay line) down the chain
+        _neighbour_exchange(dist, turned[-1:].contiguous() if first_chunk + M < plan.nchunks else None, incoming)
     if first_chunk == 0 and M == 1:                                 # the whole stream is chunk 0: already exact
         res = dict(scan)
         res["soft"] = torch.cat((_as_tensor(head, soft_b.device), row0))
         res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
         return res
     eng.import_rows(torch.cat((incoming, turned[:-1])))
+    ph.mark("state_hand_off")
     soft_c, q_c, n_c, base_c = _rows4(eng.pass_c())
+    ph.mark("pass_c_final")
     shifted = dataclasses.replace(plan, cut_shift=plan.overlap)
     if first_chunk == 0:
         # rows 0 and 1 are one exact trajectory: the head, row 0's pass-B symbols, then row 1's pass-C symbols up
@@ -607,6 +637,7 @@ def run_handoff(eng, plan, first_chunk=0, dist=None, oqpsk_half=None):
         res["soft"] = torch.cat((_as_tensor(head, soft_c.device), row0, res["soft"]))
     else:
         res = stitch(soft_c, q_c, n_c, shifted, first_chunk=first_chunk, dist=dist, base=base_c, oqpsk_half=oqpsk_half)
+    ph.mark("join")
     res["first_pass"] = dict(k=scan["k"], agreement=scan["agreement"], K=K)
     return res
 
@@ -651,11 +682,12 @@ class ShardedDemod:
         self.eng = GpuEngine(raw, plan, device=device, first_chunk=self.c0, nchunks=self.c1 - self.c0,
                              raw_first=raw_first, seed_carrier=seed_carrier, **cfg)
 
-    def run(self):
+    def run(self, phase_ms=None):
+        """phase_ms: optional dict that receives the wall time of each phase in ms (hand-off scheme)."""
         eng, plan, c0, M = self.eng, self.plan, self.c0, self.c1 - self.c0
         l0 = eng.d.launch_count()
         if self.handoff:
-            res = run_handoff(eng, plan, first_chunk=c0, dist=self.dist, oqpsk_half=self.oqpsk_half)
+            res = run_handoff(eng, plan, first_chunk=c0, dist=self.dist, oqpsk_half=self.oqpsk_half, phase_ms=phase_ms)
         elif not self.two_pass:
             res = _stitch_rows(eng.run(), plan, first_chunk=c0, dist=self.dist)
         else:

@@ -128,13 +128,16 @@ def wav_header(data_bytes, fs=230000, bps=16, channels=2):
 
 
 def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 72000, seed=7,
-                   esn0_db=12.0, rms=6000.0, device="cuda", out=None, group=64):
+                   esn0_db=12.0, rms=6000.0, device="cuda", out=None, group=64, cfo_max_hz=1500.0, row_items=None):
     """Build `nstreams` distinct raw streams on the device from one tileable baseband period.
 
     Stream b = period rolled by a per-stream shift, tiled to nsamples, mixed with a per-stream
-    carrier (multiple of fs/len(period) so tiling stays seamless), own phase, amplitude and noise.
-    Returns a torch tensor [nstreams, 2*nsamples] of the raw dtype. Plumbing only (torch ops,
-    `group` streams per batch of ops).
+    carrier (multiple of fs/len(period) so tiling stays seamless; |offset| <= cfo_max_hz), own phase,
+    amplitude and noise. Returns a torch tensor [nstreams, 2*nsamples] of the raw dtype (a view of rows
+    `row_items` items long when given: rows whose byte length is not a multiple of 16 need a padded
+    stride for the library's vector loads). Plumbing only (torch ops, `group` streams per batch of ops).
+    With nsamples == len(period) a row is exactly one period of a periodic signal: replaying it again
+    and again is ONE continuous stream (bench.py's locked pass).
     """
     import torch
 
@@ -142,12 +145,15 @@ def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 7
     P = int(period.size)
     base = torch.from_numpy(np.ascontiguousarray(period.astype(np.complex64))).to(device)
     if out is None:
-        out = torch.empty((nstreams, 2 * nsamples), dtype=dt, device=device)
+        if row_items is None:
+            out = torch.empty((nstreams, 2 * nsamples), dtype=dt, device=device)
+        else:
+            out = torch.zeros((nstreams, row_items), dtype=dt, device=device)[:, : 2 * nsamples]
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     rs = np.random.Generator(np.random.PCG64(seed))
     step = fs / P
-    kmax = int(1500 / step)
+    kmax = int(cfo_max_hz / step)
     shift = torch.from_numpy(rs.integers(0, P, nstreams)).to(device)
     cfo = torch.from_numpy(step * rs.integers(-kmax, kmax + 1, nstreams).astype(np.float64)).to(device)
     ph = torch.from_numpy(rs.uniform(0, 2 * np.pi, nstreams)).to(device)

@@ -261,6 +261,32 @@ retime(lrpt_oracle_t *o, float cur)
 	o->t_freq = o->t_center + fd;
 }
 
+/* filter_fwd_sample + filter_get (filter.c:39-65) for EVERY (sample, sub-step) of a block that starts from the
+ * zeroed delay line of filter_init_rrc: out[(n*L + i)*2 + {0,1}] = re, im of filter_get(flt, i) after sample n was
+ * pushed. The checker of the stand-alone FIR stage (csrc/fir_stage.cu); does not touch the oracle's state. */
+int
+lrpt_oracle_fir_all(const lrpt_oracle_t *o, const void *raw, long nsamples, float *out)
+{
+	const uint8_t *u8 = raw; const int16_t *s16 = raw; const float *f32 = raw;
+	const int taps = o->taps, L = o->interp, H = taps - 1;
+	float *work = calloc(2*(size_t)(H + nsamples), sizeof(float));
+	long n;
+	int i;
+	if (!work) return 1;
+	for (n=0; n<nsamples; n++) {
+		float re, im;
+		if (o->bps == 8)       { re = (float)((int)u8[2*n] - 128); im = (float)((int)u8[2*n+1] - 128); }
+		else if (o->bps == 16) { re = (float)s16[2*n]; im = (float)s16[2*n+1]; }
+		else                   { re = f32[2*n]; im = f32[2*n+1]; }
+		work[2*(H+n)] = re; work[2*(H+n)+1] = im;
+	}
+	for (n=0; n<nsamples; n++)
+		for (i=0; i<L; i++)
+			fir_point(work + 2*n, o->h + (L-1-i)*taps, taps, out + 2*((size_t)n*L + i), out + 2*((size_t)n*L + i) + 1);
+	free(work);
+	return 0;
+}
+
 /* ------------------------------------------------------------- process -- */
 
 #define BLOCK 32768

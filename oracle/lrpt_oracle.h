@@ -65,6 +65,10 @@ long lrpt_oracle_process(lrpt_oracle_t *o, const void *raw, long nsamples,
                          float *sym, int8_t *soft, long long *sample_idx,
                          uint8_t *lock_once, long cap);
 
+/* filter_get (filter.c:46-65) at every (sample, sub-step) of a block from a zeroed delay line:
+ * out[(n*interp + i)*2 + {0,1}]; checker of the stand-alone FIR stage. 0 on success. */
+int  lrpt_oracle_fir_all(const lrpt_oracle_t *o, const void *raw, long nsamples, float *out);
+
 /* building blocks, exported for known-answer tests */
 float   lrpt_oracle_rrc_coeff(int stage_no, unsigned taps, float osf, float alpha);  /* filter.c:71-94 */
 float   lrpt_oracle_fast_sin(float x);                                                /* sincos.c:13-34 */

@@ -112,6 +112,8 @@ class Oracle:
             L.lrpt_oracle_process.restype = C.c_long
             L.lrpt_oracle_rrc_coeff.argtypes = [C.c_int, C.c_uint, C.c_float, C.c_float]
             L.lrpt_oracle_rrc_coeff.restype = C.c_float
+            L.lrpt_oracle_fir_all.argtypes = [C.POINTER(_OracleStruct), C.c_void_p, C.c_long, C.c_void_p]
+            L.lrpt_oracle_fir_all.restype = C.c_int
             for f in ("lrpt_oracle_fast_sin", "lrpt_oracle_fast_cos"):
                 getattr(L, f).argtypes = [C.c_float]
                 getattr(L, f).restype = C.c_float
@@ -155,6 +157,15 @@ class Oracle:
             res["q"] = res.sample_idx * self.s.interp + sub[: res.sample_idx.size].astype(np.int64)
         return res
 
+    def fir_all(self, raw):
+        """filter_get at every (sample, sub-step) from a zeroed delay line: float32 [nsamples, interp, 2]."""
+        a = _as_raw(raw, self.bps)
+        n = a.size // 2
+        out = np.empty((n, self.s.interp, 2), np.float32)
+        if self.L.lrpt_oracle_fir_all(C.byref(self.s), a.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)):
+            raise MemoryError("lrpt_oracle_fir_all")
+        return out
+
     def taps(self):
         n = self.s.taps * self.s.interp
         return np.ctypeslib.as_array(self.s.h, (n,)).copy()
@@ -190,18 +201,32 @@ class _RefState(C.Structure):
 
 
 class Ref:
-    """The compiled reference. One private copy of the .so per instance => fresh statics."""
+    """The compiled reference. One private copy of the .so per instance => fresh statics.
+
+    in_place=True loads oracle/_ref/libref_<kind>.so itself (ONE instance per process; the file shows up in the
+    process's memory map, which is how the driver tells the reference arm of bench.py from a fallback) and
+    enables power_on(): back to the state of a freshly loaded library, for many power-on streams in one process."""
 
     def __init__(self, samplerate=230000, symrate=72000, interp=5, order=32, oqpsk=0, bps=16,
-                 pll_bw=1.0, sym_bw=0.00005, freq_max=-1.0, kind="strict"):
+                 pll_bw=1.0, sym_bw=0.00005, freq_max=-1.0, kind="strict", in_place=False):
         src = os.path.join(REF_DIR, "libref_%s.so" % kind)
         if not os.path.exists(src):
             raise FileNotFoundError(src + " (run `make -C oracle ref` where /root/reference exists)")
-        fd, self._tmp = tempfile.mkstemp(prefix="libref_", suffix=".so")
-        os.close(fd)
-        shutil.copyfile(src, self._tmp)
-        L = self.L = C.CDLL(self._tmp)
-        os.unlink(self._tmp)             # mapping stays valid; nothing left on disk
+        self._init_args = (pll_bw, sym_bw, samplerate, int(symrate), interp, order, oqpsk, freq_max)
+        if in_place:
+            L = self.L = C.CDLL(src)
+            L.ref_save_power_on.restype = C.c_int
+            L.ref_power_on.restype = C.c_int
+            if L.ref_save_power_on():
+                raise RuntimeError("ref_save_power_on failed")
+            L.ref_power_on()             # a second in-place instance in the same process starts fresh as well
+        else:
+            fd, self._tmp = tempfile.mkstemp(prefix="libref_", suffix=".so")
+            os.close(fd)
+            shutil.copyfile(src, self._tmp)
+            L = self.L = C.CDLL(self._tmp)
+            os.unlink(self._tmp)             # mapping stays valid; nothing left on disk
+        self._in_place = in_place
         L.ref_init.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         L.ref_process.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_long]
@@ -228,6 +253,14 @@ class Ref:
         fn = lambda p, n, sym, soft, idx, lock, cap_: self.L.ref_process(
             p, n, self.bps, sym, soft, idx, lock, cap_)
         return _run(fn, raw, self.bps, cap, want_float)
+
+    def power_on(self):
+        """Fresh process image of every static of the reference, then demod_init again (in_place instances)."""
+        if not self._in_place:
+            raise RuntimeError("power_on needs in_place=True")
+        if self.L.ref_power_on():
+            raise RuntimeError("ref_power_on failed")
+        self.L.ref_init(*self._init_args)
 
     def taps(self):
         n = self.L.ref_get_taps(None, 0)

@@ -16,8 +16,15 @@
  * Fresh state: the reference has no re-init for AGC (agc.c:9-10), the OQPSK
  * `state`/`inphase` function statics (timing.c:43, demod.c:54) or `updown`
  * (pll.c:112). The python wrapper therefore dlopen()s a private temp copy of
- * the built .so for every new demodulator instance.
+ * the built .so for every new demodulator instance -- or, for many power-on
+ * streams in one process (bench.py's reference arm), loads the library once and
+ * calls ref_save_power_on() / ref_power_on(): the harness keeps a copy of this
+ * library's own writable data (.data + .bss, found with dl_iterate_phdr) as it is
+ * right after loading and puts it back, which is exactly a fresh process image
+ * for every static of the reference, function-scope ones included.
  */
+#define _GNU_SOURCE
+#include <link.h>
 #include <complex.h>
 #include <math.h>
 #include <stdint.h>
@@ -52,6 +59,61 @@ typedef struct {
 } ref_state_t;
 
 static int g_oqpsk;
+
+/* ---- power-on image of the library's writable data (harness bookkeeping lives on the heap) ---- */
+typedef struct { char *lo, *hi, *copy; } ref_image_t;
+static ref_image_t *g_image;
+
+static int
+find_data_segment(struct dl_phdr_info *info, size_t size, void *data)
+{
+	ref_image_t *im = data;
+	const char *probe = (const char *)&g_oqpsk;
+	char *relro_hi = NULL;
+	int i;
+	(void)size;
+	for (i=0; i<info->dlpi_phnum; i++) {
+		const ElfW(Phdr) *ph = &info->dlpi_phdr[i];
+		if (ph->p_type == PT_GNU_RELRO)                       /* read-only after relocation: never written back */
+			relro_hi = (char *)info->dlpi_addr + ph->p_vaddr + ph->p_memsz;
+	}
+	for (i=0; i<info->dlpi_phnum; i++) {
+		const ElfW(Phdr) *ph = &info->dlpi_phdr[i];
+		char *lo = (char *)info->dlpi_addr + ph->p_vaddr, *hi = lo + ph->p_memsz;
+		if (ph->p_type != PT_LOAD || !(ph->p_flags & PF_W) || probe < lo || probe >= hi) continue;
+		if (relro_hi && relro_hi > lo && relro_hi <= hi)
+			lo = relro_hi;                                    /* the loader protects whole pages BELOW this address only */
+		im->lo = lo; im->hi = hi;
+		return 1;
+	}
+	return 0;
+}
+
+/* Call once, right after loading the library and before ref_init. 0 on success. */
+int
+ref_save_power_on(void)
+{
+	ref_image_t *im;
+	if (g_image) return 0;
+	im = calloc(1, sizeof(*im));
+	if (!im || !dl_iterate_phdr(find_data_segment, im) || !im->lo) { free(im); return -1; }
+	im->copy = malloc((size_t)(im->hi - im->lo));
+	if (!im->copy) { free(im); return -1; }
+	g_image = im;                                             /* part of the image: saved as "set" */
+	memcpy(im->copy, im->lo, (size_t)(im->hi - im->lo));
+	return 0;
+}
+
+/* Back to the state of a freshly loaded library (then call ref_init again). 0 on success. */
+int
+ref_power_on(void)
+{
+	ref_image_t *im = g_image;
+	if (!im) return -1;
+	demod_deinit();                                           /* frees the filter the image does not know about */
+	memcpy(im->lo, im->copy, (size_t)(im->hi - im->lo));
+	return 0;
+}
 
 void
 ref_init(float pll_bw, float sym_bw, int samplerate, int symrate, int interp,
