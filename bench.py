@@ -443,7 +443,9 @@ def main():
 
     # ---- value_locked: steady state. Every row is ONE period of a periodic signal (len(period) == samples per
     # row, carrier a multiple of fs/len), so replaying the row with the state carried over is one continuous
-    # stream; |carrier offset| <= 150 Hz, three untimed steps of pre-roll: the loops are locked when timing starts.
+    # stream; carrier offset 0..+150 Hz (the reference's acquisition sweep starts upwards at 1e-6 rad/symbol^2,
+    # pll.c:126: an offset below zero is found only after the sweep has been to +3.4 kHz and back, ~600 k symbols),
+    # three untimed steps of pre-roll: the loops are locked when timing starts.
     locked = None
     if not a.no_locked:
         NL = (N // 115) * 115 + (115 if N % 115 else 0)      # samples per row with NL*symrate/fs integral (72k and 80k)
@@ -452,7 +454,7 @@ def main():
         per_l = synth.baseband(NL, symrate=symrate, oqpsk=bool(oqpsk), periodic=True, seed=5).astype(np.complex64)
         items = (2 * NL * (bps // 8) + 15) // 16 * 16 // (bps // 8)
         raw_l = synth.device_streams(per_l, B, NL, bps=bps, sps=FS / symrate, seed=70 + rank, device="cuda",
-                                     cfo_max_hz=150.0, row_items=items)
+                                     cfo_min_hz=0.0, cfo_max_hz=150.0, row_items=items)
 
         def locked_frac():
             buf = torch.empty(d.states_size(), dtype=torch.uint8, device="cuda")
@@ -495,7 +497,7 @@ def main():
                   "locked_frac_at_start": lf0, "locked_frac_at_end": lf1, "gpu_launches": int(launches_l),
                   "oracle_check_4_streams_continuous": check_l,
                   "workload": "the same %d streams/GPU, state carried from step to step (no reset): each row is one period of a "
-                              "periodic signal, |carrier offset| <= 150 Hz" % B}
+                              "periodic signal, carrier offset 0..+150 Hz" % B}
         del raw_l
     d.close()
     del soft, nsym

@@ -122,14 +122,62 @@ struct wave_header {                          /* wavfile.c:16-31 */
 	char data[4]; uint32_t subchunk2_size;
 };
 
+/* wavfile.c:34-49 for the canonical 44-byte header -- the only form the reference understands, and for it
+ * this function consumes exactly the bytes the reference consumes. Anything else that IS a RIFF/WAVE file
+ * (an 18- or 40-byte `fmt ` chunk, WAVE_FORMAT_EXTENSIBLE, `LIST`/`fact`/`bext` chunks before `data`) the
+ * reference would take for canonical and demodulate the rest of the header as samples, shifting I against Q;
+ * here the chunks are walked properly (sequential reads only, so it works on a pipe) and the stream is left
+ * at the first byte of the `data` payload. Returns 0 on success, 1 if this is not a 2-channel WAV. */
 static int
-wav_parse(FILE *fd, int *samplerate, int *bps)       /* wavfile.c:34-49 */
+wav_parse(FILE *fd, int *samplerate, int *bps)
 {
 	struct wave_header h;
+	uint8_t ck[8], fmt[40];
+	uint32_t size;
+	int have_fmt = 1;
 	if (!fread(&h, sizeof(h), 1, fd)) return 1;
-	if (strncmp(h.riff, "RIFF", 4) || strncmp(h.wave, "WAVE", 4) || h.num_channels != 2) return 1;
-	if (!(*bps = h.bits_per_sample)) return 1;
-	*samplerate = (int)h.sample_rate;
+	if (strncmp(h.riff, "RIFF", 4) || strncmp(h.wave, "WAVE", 4)) return 1;
+	if (!strncmp(h.fmt, "fmt ", 4) && h.subchunk_size == 16 && !strncmp(h.data, "data", 4)) {   /* canonical */
+		if (h.num_channels != 2 || !(*bps = h.bits_per_sample)) return 1;
+		*samplerate = (int)h.sample_rate;
+		return 0;
+	}
+	/* general RIFF walk; 44 bytes are already consumed: re-read them from the struct */
+	{
+		const uint8_t *raw = (const uint8_t *)&h;
+		size_t pos = 12;                                       /* first chunk header */
+		uint16_t channels = 0, bits = 0; uint32_t rate = 0;
+		have_fmt = 0;
+		for (;;) {
+			size_t i;
+			for (i = 0; i < 8; i++, pos++) {                   /* chunk id + size, from the buffer or the stream */
+				if (pos < sizeof(h)) ck[i] = raw[pos];
+				else { int c = fgetc(fd); if (c == EOF) return 1; ck[i] = (uint8_t)c; }
+			}
+			size = (uint32_t)ck[4] | (uint32_t)ck[5] << 8 | (uint32_t)ck[6] << 16 | (uint32_t)ck[7] << 24;
+			if (!memcmp(ck, "data", 4)) {
+				if (pos < sizeof(h)) return 1;                 /* payload would start inside what was read as header: not handled */
+				break;
+			}
+			{
+				const size_t padded = (size_t)size + (size & 1);
+				for (i = 0; i < padded; i++, pos++) {
+					int c;
+					if (pos < sizeof(h)) c = raw[pos];
+					else if ((c = fgetc(fd)) == EOF) return 1;
+					if (!memcmp(ck, "fmt ", 4) && i < sizeof(fmt)) fmt[i] = (uint8_t)c;
+				}
+			}
+			if (!memcmp(ck, "fmt ", 4) && size >= 16) {
+				channels = (uint16_t)(fmt[2] | fmt[3] << 8);
+				rate = (uint32_t)fmt[4] | (uint32_t)fmt[5] << 8 | (uint32_t)fmt[6] << 16 | (uint32_t)fmt[7] << 24;
+				bits = (uint16_t)(fmt[14] | fmt[15] << 8);
+				have_fmt = 1;
+			}
+		}
+		if (!have_fmt || channels != 2 || !bits) return 1;
+		*bps = bits; *samplerate = (int)rate;
+	}
 	return 0;
 }
 

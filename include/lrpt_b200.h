@@ -234,6 +234,17 @@ typedef struct lrpt_shard_report {
 int  lrpt_sharded_process(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
                           int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep);
 
+/* ---- page-locked host buffers ---------------------------------------------------------------------
+ * The host-buffer entry points (lrpt_process, lrpt_process_batch, lrpt_sharded_process) copy at the full
+ * speed of the host link only from / to page-locked memory; from ordinary malloc memory the driver stages
+ * every copy through its own bounce buffer (measured: 470 ms instead of 80 ms for a 4.3 GB recording).
+ * The reference reads into a static 32 KiB buffer (wavfile.c:8,55); a host that wants the link's speed
+ * allocates its slabs here (or pins memory it already has). NULL / LRPT_ERR_CUDA when the driver refuses. */
+void *lrpt_alloc_host(size_t bytes);
+void  lrpt_free_host(void *p);
+int   lrpt_pin_host(void *p, size_t bytes);       /* cudaHostRegister on caller-owned memory */
+int   lrpt_unpin_host(void *p);
+
 /* ---- the feed-forward stage alone (csrc/fir_stage.cu) ----------------------------------------------
  * filter_fwd_sample + filter_get (filter.c:39-65) for EVERY (sample n, timing sub-step i) of `nrows` rows,
  * device buffers: d_out[row][n*L + i] = the complex value filter_get(flt, i) returns after sample n of the

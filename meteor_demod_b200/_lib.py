@@ -82,6 +82,10 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrpt_sharded_process": (C.c_int, [C.POINTER(Params), C.POINTER(ShardPlan), C.c_void_p, C.c_size_t, C.c_void_p,
                                        C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(ShardReport)]),
+    "lrpt_alloc_host": (C.c_void_p, [C.c_size_t]),
+    "lrpt_free_host": (None, [C.c_void_p]),
+    "lrpt_pin_host": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "lrpt_unpin_host": (C.c_int, [C.c_void_p]),
     "lrpt_fir_stage_device": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p,
                                         C.c_size_t, C.c_int, C.c_void_p]),
     "lrpt_describe": (C.c_int, [C.POINTER(Params), C.POINTER(State), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -28,6 +28,13 @@ namespace lrpt {
 #ifndef LRPT_SPEC_PIPE
 #define LRPT_SPEC_PIPE 1          /* 1: symbol step split in two (demod_core.cuh), as in demod_ws.cu */
 #endif
+#ifndef LRPT_SPEC_SPLIT
+#define LRPT_SPEC_SPLIT 0         /* 1: timing / loop / egress warps as in demod_ws.cu (ws_common.cuh). Measured on B200
+                                     (profiles/r2_recurrence_split_ab.log): it wins below ~16 streams per SM, where demod_ws.cu
+                                     is used anyway, and loses at 32 streams per SM, where the five FIR warps it costs are
+                                     missed (19.7 vs 22.2 GS/s at 4736 streams) -- so this kernel keeps one recurrence warp */
+#endif
+constexpr int SP_P = LRPT_SPEC_SPLIT ? 7 : WS_PRODUCERS;   /* FIR warps */
 constexpr int SP_SLOTS  = 2;      /* candidate tile ring depth                       */
 constexpr int SP_NC     = 3;      /* candidate sub-steps per predicted event         */
 constexpr int SP_KMAX   = 12;     /* predicted events per stream and tile            */
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 {
 	constexpr int LP = SpTapPad<L>::value;
-	constexpr int S = SP_SLOTS, P = WS_PRODUCERS, KM = SP_KMAX, NC = SP_NC;
+	constexpr int S = SP_SLOTS, P = SP_P, KM = SP_KMAX, NC = SP_NC;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
 	const int taps = c.taps, H = taps - 1;
@@ -97,7 +104,11 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 	uint64_t *full  = reinterpret_cast<uint64_t *>(smem_raw);       /* [S] */
 	uint64_t *empty = full + S;                                     /* [S] */
 	float *lut = reinterpret_cast<float *>(empty + S);              /* [32] */
-	float *hT  = lut + 32;                                          /* [taps][LP] */
+	MsgRD *r2d = reinterpret_cast<MsgRD *>(lut + 32);               /* [32] timing warp -> loop warp */
+	MsgDR *d2r = reinterpret_cast<MsgDR *>(r2d + 32);               /* [32] loop warp -> timing warp */
+	MsgDE *d2e = reinterpret_cast<MsgDE *>(d2r + 32);               /* [EG_RING][32] loop warp -> egress warp */
+	volatile int *eack = reinterpret_cast<volatile int *>(d2e + EG_RING*32);   /* [32] rounds the egress warp has consumed */
+	float *hT  = reinterpret_cast<float *>(const_cast<int *>(eack) + 32);      /* [taps][LP] */
 	float4 *pubs = reinterpret_cast<float4 *>(hT + ((taps*LP + 3) & ~3));     /* [G] published timing state */
 	float2 *wins = reinterpret_cast<float2 *>(pubs + a.G);          /* [G][wstride] delay-line windows */
 	float2 *cand = wins + (size_t)a.G*wstride;                      /* [G][S][KM][NC] candidate FIR outputs */
@@ -107,7 +118,12 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 		for (int s = 0; s < S; s++) { mbar_init(&full[s], P); mbar_init(&empty[s], 1); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	if (threadIdx.x < 32) lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
+	if (threadIdx.x < 32) {
+		lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
+		r2d[threadIdx.x].seq = -1; d2r[threadIdx.x].seq = -1;         /* no round yet */
+		eack[threadIdx.x] = -1;
+	}
+	for (int i = threadIdx.x; i < EG_RING*32; i += WS_THREADS) d2e[i].seq = -1;
 	for (int i = threadIdx.x; i < taps*LP; i += WS_THREADS) {
 		const int k = i/LP, p = i - k*LP;
 		hT[i] = (p < L) ? a.taps[p*taps + k] : 0.0f;
@@ -115,6 +131,88 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 	for (int i = threadIdx.x; i < a.G; i += WS_THREADS) pubs[i] = make_float4(__int_as_float(-1), 0.f, 1.f, 0.f);
 	__syncthreads();
 
+#if LRPT_SPEC_SPLIT
+	if (warp >= 4 && (warp & 3) < 2) return;                        /* sub-partitions 0 and 1: timing warp, loop warp */
+	if (warp == 1) {
+		loop_warp_run<OQ>(c, a, lut, r2d, d2r, d2e, eack, lane, lane < Gc, g0);
+	} else if (warp == 2) {
+		egress_warp_run(a, d2e, eack, lane, lane < Gc, g0);
+	} else if (warp == 0) {
+		/* ===================== timing warp "R" (ws_common.cuh, two-warp recurrence) ===================== */
+		const bool active = lane < Gc;
+		const int local = g0 + lane;
+		const int sid = a.first_stream + local;
+		Loop r;
+		unsigned misses = 0;
+		loop_load(r, a.states[a.first_stream + (active ? local : g0)]);
+		const int Qend = a.nsamples*L;
+		int Q = 0;
+		bool have_x = false; int Qx = 0, half = 0;
+		const float2 *my_win = wins + (size_t)lane*wstride + 1;     /* +1: guard entry in front */
+		const float2 *my_cand = cand + (size_t)lane*SP_CSTR;
+		const int *my_ck = cks + (size_t)lane*SP_KSTR;
+		int round = 0;
+		for (int t = 0; t < ntiles; t++) {
+			const int slot = t % S;
+			mbar_wait(&full[slot], (unsigned)(t/S) & 1u);
+			const int q1 = min((t + 1)*T, a.nsamples)*L;
+			const float2 *tc = my_cand + slot*KM*NC;
+			const int *tk = my_ck + slot*KM;
+			int ks = 0;
+			int ckn = -0x40000000;
+			float2 c0 = make_float2(0.f, 0.f), c1 = c0, c2 = c0;
+			if (active) { ckn = tk[0]; c0 = tc[0]; c1 = tc[1]; c2 = tc[2]; }
+			if (active && !have_x && Q < q1)
+				have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
+			while (true) {
+				__syncwarp();
+				const bool ready = active && have_x && Qx < q1;
+				if (!__any_sync(0xffffffffu, ready)) break;
+				round++;
+				float2 y = make_float2(0.f, 0.f);
+				bool hit = false;
+				if (ready) {
+					/* filter_get(flt, i) for sub-step Qx: from the candidates, or evaluated here */
+					while (ks < KM - 1 && ckn + 1 < Qx) {
+						ks++;
+						ckn = tk[ks]; c0 = tc[ks*NC]; c1 = tc[ks*NC + 1]; c2 = tc[ks*NC + 2];
+					}
+					const int d = Qx - ckn + 1;
+					hit = d >= 0 && d < NC;
+					if (hit) y = (d == 0) ? c0 : (d == 1) ? c1 : c2;
+					else {
+						const int n = Qx/L, i = Qx - n*L;
+						y = fir_single<LP>(my_win + (t % NT)*T + (n - t*T), hT, taps, L - 1 - i);
+						misses++;
+					}
+				}
+				__syncwarp();
+				const int Qsym = Qx;
+				timing_round<OQ>(r, c, ready, y, round, r2d, d2r, lane, a.nco_n0, Q, q1, Qend, Qx, half, have_x);
+				if (ready) {
+					/* publish the timing state the FIR warps extrapolate from */
+					pubs[lane] = make_float4(__int_as_float(Qsym), r.t_phase, r.t_freq, nco_threshold(r, c));
+					if (hit) {                                       /* the next event will look at the next entry */
+						if (ks < KM - 1) {
+							ks++;
+							ckn = tk[ks]; c0 = tc[ks*NC]; c1 = tc[ks*NC + 1]; c2 = tc[ks*NC + 2];
+						} else ckn = -0x40000000;
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty[slot]);
+		}
+		round++;
+		mbox_put4(&r2d[lane], 0.0f, 0.0f, MSG_STOP, round);
+		if (active) {                                               /* this warp's half of the state */
+			lrpt_state_t &s = a.states[sid];
+			s.t_phase = r.t_phase; s.t_freq = r.t_freq; s.t_prev = r.t_prev; s.t_dual_state = r.t_dual;
+			s.agc_bias_re = r.bias_re; s.agc_bias_im = r.bias_im;
+			if (a.miss_count && misses) atomicAdd(a.miss_count, (unsigned long long)misses);
+		}
+	} else {
+#else
 	if (warp != 0 && (warp & 3) == 0) return;                       /* sub-partition 0 belongs to the recurrence warp */
 	if (warp == 0) {
 		/* ===================== recurrence warp: one lane per stream ===================== */
@@ -279,8 +377,13 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 			if (a.miss_count && misses) atomicAdd(a.miss_count, (unsigned long long)misses);
 		}
 	} else {
+#endif
 		/* ===================== FIR warps: ingest + speculative FIR ===================== */
+#if LRPT_SPEC_SPLIT
+		const int pw = (warp >> 2)*2 + (warp & 3) - 3;              /* warps 3, 6,7, 10,11, 14,15 -> 0..P-1 */
+#else
 		const int pw = (warp >> 2)*3 + (warp & 3) - 1;              /* 0..P-1 */
+#endif
 		const int ptid = pw*32 + lane;
 		constexpr int MAXU = (SP_MAX_G + P - 1)/P;                   /* ingest units (streams) per warp */
 		const int npairs = Gc*KM;                                   /* (stream, predicted event) pairs per tile */
@@ -299,7 +402,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 			}
 			wins[(size_t)g*wstride + 1 + j] = v;
 		}
-		producers_sync();
+		producers_sync<P>();
 
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
@@ -424,7 +527,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 					}
 				}
 			}
-			producers_sync();
+			producers_sync<P>();
 		}
 
 		const int e_last = (ntiles - 1)/NT;
@@ -454,7 +557,7 @@ static int sp_nt(int taps, int T) { return 4 + (taps - 1 + T - 1)/T; }
 static size_t sp_fixed_smem(int taps, int L)
 {
 	const int LP = (L <= 4) ? 4 : 8;
-	return 2*SP_SLOTS*sizeof(uint64_t) + 32*sizeof(float) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
+	return 2*SP_SLOTS*sizeof(uint64_t) + 32*sizeof(float) + 32*(sizeof(MsgRD) + sizeof(MsgDR) + sizeof(int)) + EG_RING*32*sizeof(MsgDE) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
 }
 
 static size_t sp_stream_smem(int taps, int T)

@@ -28,6 +28,11 @@ namespace lrpt {
 #ifndef LRPT_WS_PIPE
 #define LRPT_WS_PIPE 1             /* 1: symbol step split in two, deferred half side by side with the next NCO search */
 #endif
+#ifndef LRPT_WS_SPLIT
+#define LRPT_WS_SPLIT 1            /* 1: the two halves of the symbol step on two warps (ws_common.cuh, "two-warp recurrence") */
+#endif
+/* FIR warps: with the two-warp recurrence SM sub-partitions 0 and 1 belong to the timing warp and the loop warp */
+constexpr int WS_P = LRPT_WS_SPLIT ? 7 : WS_PRODUCERS;
 constexpr int WS_T        = 32;    /* samples per tile = one FIR unit per stream  */
 constexpr int WS_SLOTS    = 2;     /* FIR tile ring depth                        */
 constexpr int WS_MAX_G    = 32;    /* streams per CTA = consumer lanes           */
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM)
 demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 {
 	constexpr int LP = TapPad<L>::value;
-	constexpr int T = WS_T, S = WS_SLOTS, P = WS_PRODUCERS;
+	constexpr int T = WS_T, S = WS_SLOTS, P = WS_P;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
 	const int taps = c.taps, H = taps - 1;
@@ -109,7 +114,11 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 	uint64_t *full  = reinterpret_cast<uint64_t *>(smem_raw);       /* [S] */
 	uint64_t *empty = full + S;                                     /* [S] */
 	float *lut = reinterpret_cast<float *>(empty + S);              /* [32] */
-	float *hT  = lut + 32;                                          /* [taps][LP] */
+	MsgRD *r2d = reinterpret_cast<MsgRD *>(lut + 32);               /* [32] timing warp -> loop warp */
+	MsgDR *d2r = reinterpret_cast<MsgDR *>(r2d + 32);               /* [32] loop warp -> timing warp */
+	MsgDE *d2e = reinterpret_cast<MsgDE *>(d2r + 32);               /* [EG_RING][32] loop warp -> egress warp */
+	volatile int *eack = reinterpret_cast<volatile int *>(d2e + EG_RING*32);   /* [32] rounds the egress warp has consumed */
+	float *hT  = reinterpret_cast<float *>(const_cast<int *>(eack) + 32);      /* [taps][LP] */
 	float2 *wins  = reinterpret_cast<float2 *>(hT + ((taps*LP + 3) & ~3));   /* [G][win]  delay-line windows */
 	float2 *tiles = wins + (size_t)a.G*win;                         /* [G][S][T*L] FIR outputs */
 
@@ -117,7 +126,12 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 		for (int s = 0; s < S; s++) { mbar_init(&full[s], P); mbar_init(&empty[s], 1); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	if (threadIdx.x < 32) lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
+	if (threadIdx.x < 32) {
+		lut[threadIdx.x] = c.lut_tanh[threadIdx.x];
+		r2d[threadIdx.x].seq = -1; d2r[threadIdx.x].seq = -1;         /* no round yet */
+		eack[threadIdx.x] = -1;
+	}
+	for (int i = threadIdx.x; i < EG_RING*32; i += WS_THREADS) d2e[i].seq = -1;
 	for (int i = threadIdx.x; i < taps*LP; i += WS_THREADS) {
 		const int k = i/LP, p = i - k*LP;
 		hT[i] = (p < L) ? a.taps[p*taps + k] : 0.0f;
@@ -130,6 +144,53 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 	 * warps 4, 8, 12 retire at once and the twelve FIR warps fill sub-partitions 1-3, where they
 	 * are issue-bound without slowing the recurrence down.
 	 */
+#if LRPT_WS_SPLIT
+	if (warp >= 4 && (warp & 3) < 2) return;                        /* sub-partitions 0 and 1: timing warp, loop warp */
+	if (warp == 1) {
+		loop_warp_run<OQ>(c, a, lut, r2d, d2r, d2e, eack, lane, lane < Gc, g0);
+	} else if (warp == 2) {
+		egress_warp_run(a, d2e, eack, lane, lane < Gc, g0);
+	} else if (warp == 0) {
+		/* ===================== timing warp "R": timing NCO, delay-line pick, bias, scale, mix, retime ===================== */
+		const bool active = lane < Gc;
+		const int local = g0 + lane;
+		const int sid = a.first_stream + local;
+		Loop r;
+		loop_load(r, a.states[a.first_stream + (active ? local : g0)]);
+		const int Qend = a.nsamples*L;
+		int Q = 0;
+		bool have_x = false; int Qx = 0, half = 0;
+		const float2 *my_tiles = tiles + (size_t)lane*S*T*L;
+		int round = 0;
+		for (int t = 0; t < ntiles; t++) {
+			const int slot = t % S;
+			mbar_wait(&full[slot], (unsigned)(t/S) & 1u);
+			const int q0 = t*T*L;
+			const int q1 = min((t + 1)*T, a.nsamples)*L;
+			const float2 *tile = my_tiles + slot*T*L;
+			if (active && !have_x && Q < q1)
+				have_x = nco_to_crossing(r, c, a.nco_n0, Q, q1, Qend, Qx, half);
+			while (true) {
+				__syncwarp();
+				const bool ready = active && have_x && Qx < q1;
+				if (!__any_sync(0xffffffffu, ready)) break;
+				round++;
+				float2 y = make_float2(0.f, 0.f);
+				if (ready) y = tile[Qx - q0];                        /* filter_get(flt, i); lanes without a stream own no tile */
+				timing_round<OQ>(r, c, ready, y, round, r2d, d2r, lane, a.nco_n0, Q, q1, Qend, Qx, half, have_x);
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty[slot]);
+		}
+		round++;
+		mbox_put4(&r2d[lane], 0.0f, 0.0f, MSG_STOP, round);
+		if (active) {                                               /* this warp's half of the state */
+			lrpt_state_t &s = a.states[sid];
+			s.t_phase = r.t_phase; s.t_freq = r.t_freq; s.t_prev = r.t_prev; s.t_dual_state = r.t_dual;
+			s.agc_bias_re = r.bias_re; s.agc_bias_im = r.bias_im;
+		}
+	} else {
+#else
 	if (warp != 0 && (warp & 3) == 0) return;
 	if (warp == 0) {
 		/* ===================== consumer: one lane per stream ===================== */
@@ -255,8 +316,13 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 			if (a.out_off) a.out_off[local] = off + nsym;
 		}
 	} else {
+#endif
 		/* ===================== producers: ingest + all-phase FIR ===================== */
+#if LRPT_WS_SPLIT
+		const int pw = (warp >> 2)*2 + (warp & 3) - 3;              /* warps 3, 6,7, 10,11, 14,15 -> 0..P-1 */
+#else
 		const int pw = (warp >> 2)*3 + (warp & 3) - 1;              /* 0..P-1 */
+#endif
 		const int ptid = pw*32 + lane;
 		constexpr int SLABS = T/32;
 		const int units = Gc*SLABS;                                 /* (stream, 32-sample slab) per tile */
@@ -281,7 +347,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 			}
 			wins[(size_t)g*win + j] = v;
 		}
-		producers_sync();
+		producers_sync<P>();
 
 		for (int t = 0; t < ntiles; t++) {
 			const int slot = t % S;
@@ -326,7 +392,7 @@ demod_ws_kernel(const lrpt_consts_t c, const WsArgs a)
 					}
 				}
 			}
-			producers_sync();
+			producers_sync<P>();
 		}
 
 		/* epilogue: the last taps-1 samples become the next call's delay line. The window still
@@ -350,7 +416,7 @@ static int g_sm_smem = 0;        /* per SM */
 static size_t ws_fixed_smem(int taps, int L)
 {
 	const int LP = (L <= 4) ? 4 : 8;
-	return 2*WS_SLOTS*sizeof(uint64_t) + 32*sizeof(float) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
+	return 2*WS_SLOTS*sizeof(uint64_t) + 32*sizeof(float) + 32*(sizeof(MsgRD) + sizeof(MsgDR) + sizeof(int)) + EG_RING*32*sizeof(MsgDE) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
 }
 
 static int ws_nt(int taps) { return 2 + (taps - 1 + WS_T - 1)/WS_T; }

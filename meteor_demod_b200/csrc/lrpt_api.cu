@@ -164,7 +164,7 @@ extern "C" int lrpt_create(lrpt_demod_t **out, const lrpt_params_t *p)
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
 		const double per_sm = (double)p->nstreams/(double)(sms > 0 ? sms : 1);
 		if (per_sm > 36.0 && lane_supported(h->c)) want = LRPT_KERNEL_LANE;
-		else if (per_sm > 16.0 && spec_supported(h->c)) want = LRPT_KERNEL_SPEC;
+		else if (per_sm > 8.0 && spec_supported(h->c)) want = LRPT_KERNEL_SPEC;   /* ws gives 5 of its 12 FIR warps to the split recurrence */
 		else if (ws_supported(h->c)) want = LRPT_KERNEL_WS;
 		else if (lane_supported(h->c)) want = LRPT_KERNEL_LANE;
 		else want = LRPT_KERNEL_SIMPLE;
@@ -599,6 +599,31 @@ extern "C" int lrpt_restore(lrpt_demod_t *h, const int32_t *quarter_turns)
 		st[s].p_phase = (float)((double)st[s].p_phase - (double)(quarter_turns[s] & 3)*1.57079632679489661923);
 	CU(h, cudaMemcpyAsync(h->d_states, st.data(), sizeof(lrpt_state_t)*ns, cudaMemcpyHostToDevice, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
+	return LRPT_OK;
+}
+
+/* ------------------------------------------------------------ host memory ---- */
+
+extern "C" void *lrpt_alloc_host(size_t bytes)
+{
+	void *p = nullptr;
+	if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+extern "C" void lrpt_free_host(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int lrpt_pin_host(void *p, size_t bytes)
+{
+	if (!p || !bytes) return LRPT_ERR_ARG;
+	if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return LRPT_ERR_CUDA; }
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_unpin_host(void *p)
+{
+	if (!p) return LRPT_ERR_ARG;
+	if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return LRPT_ERR_CUDA; }
 	return LRPT_OK;
 }
 

@@ -128,11 +128,13 @@ def wav_header(data_bytes, fs=230000, bps=16, channels=2):
 
 
 def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 72000, seed=7,
-                   esn0_db=12.0, rms=6000.0, device="cuda", out=None, group=64, cfo_max_hz=1500.0, row_items=None):
+                   esn0_db=12.0, rms=6000.0, device="cuda", out=None, group=64, cfo_max_hz=1500.0, cfo_min_hz=None,
+                   row_items=None):
     """Build `nstreams` distinct raw streams on the device from one tileable baseband period.
 
     Stream b = period rolled by a per-stream shift, tiled to nsamples, mixed with a per-stream
-    carrier (multiple of fs/len(period) so tiling stays seamless; |offset| <= cfo_max_hz), own phase,
+    carrier (multiple of fs/len(period) so tiling stays seamless; offset in [cfo_min_hz, cfo_max_hz],
+    cfo_min_hz = -cfo_max_hz by default), own phase,
     amplitude and noise. Returns a torch tensor [nstreams, 2*nsamples] of the raw dtype (a view of rows
     `row_items` items long when given: rows whose byte length is not a multiple of 16 need a padded
     stride for the library's vector loads). Plumbing only (torch ops, `group` streams per batch of ops).
@@ -155,7 +157,8 @@ def device_streams(period, nstreams, nsamples, bps=16, fs=230000, sps=230000 / 7
     step = fs / P
     kmax = int(cfo_max_hz / step)
     shift = torch.from_numpy(rs.integers(0, P, nstreams)).to(device)
-    cfo = torch.from_numpy(step * rs.integers(-kmax, kmax + 1, nstreams).astype(np.float64)).to(device)
+    kmin = -kmax if cfo_min_hz is None else int(np.ceil(cfo_min_hz / step))
+    cfo = torch.from_numpy(step * rs.integers(kmin, kmax + 1, nstreams).astype(np.float64)).to(device)
     ph = torch.from_numpy(rs.uniform(0, 2 * np.pi, nstreams)).to(device)
     amp = torch.from_numpy(rs.uniform(0.6, 1.2, nstreams).astype(np.float32)).to(device)
     n = torch.arange(nsamples, device=device)
