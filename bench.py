@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-locked", action="store_true", help="skip the steady-state (locked, state carried over) pass")
     ap.add_argument("--no-single", action="store_true", help="skip the single exact stream sub-record")
+    ap.add_argument("--no-frontend", action="store_true", help="skip the decoder front-end sub-record")
     ap.add_argument("--no-c4", action="store_true", help="skip the time-sharded single-stream sub-record (BASELINE config 4)")
     ap.add_argument("--c4-samples", type=int, default=1 << 33, help="length of the ONE stream of the c4 sub-record")
     ap.add_argument("--no-cpu", action="store_true")
@@ -508,6 +509,11 @@ def main():
     if not a.no_single:
         single = bench_single_stream(cfg, local, rank)
 
+    # ---- frontend: the decoder front-end behind the path ----------------------------------------
+    front = None
+    if not a.no_frontend:
+        front = bench_frontend(local, rank)
+
     # ---- c4: BASELINE config 4 -- ONE long stream, time-sharded over chunks and ranks with state hand-off ------
     c4 = None
     if not a.no_c4:
@@ -562,13 +568,63 @@ def main():
                          "note": "instruction-issue bound, not HBM bound (DESIGN.md section 5); the reference's own lazy "
                                  "FIR (4*taps flops per filter_get) runs at %.2f Tflop/s" % (fir_flops / (kern_ms * 1e-3) / 1e12),
                          "limiter": limiter},
-            "e2e": e2e, "value_locked": locked, "single_stream": single, "c4": c4,
+            "e2e": e2e, "value_locked": locked, "single_stream": single, "c4": c4, "frontend": front,
             "host_cores_bound_to_gpu_numa_node": numa}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_frontend(local, rank, nframes_block=64, tiles=128):
+    """SURVEY 8(f1), the step behind this path: frame synchronisation + Viterbi decoding of a device-resident soft
+    stream (csrc/frontend.cu). 8192 CADUs = 67 M symbols; every decoded payload is compared with what was sent; the
+    CPU oracle (oracle/frontend_oracle.c, one core) is timed on a bounded sample."""
+    import torch
+    from meteor_demod_b200 import frontend
+    from oracle import pyfrontend as fe
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (nframes_block, 1020), dtype=np.uint8)
+    block = fe.transmit(frames, noise=40.0, turns=1, swap=False, seed=12)            # [64*8192, 2] int8
+    soft = torch.from_numpy(block).cuda().repeat(tiles, 1).contiguous()
+    nsym = soft.shape[0]
+    nfr = nsym // fe.CADU_SYMS
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    vit = frontend.Viterbi(local)
+    best_sync, best_vit = 1e9, 1e9
+    for _ in range(3):
+        torch.cuda.synchronize()
+        ev[0].record()
+        score, hyp = frontend.sync_scores(soft)
+        off, oh, osc = frontend.window_peaks(score, hyp)
+        ev[1].record()
+        cadu, metric = vit.decode(soft, off, oh)
+        ev[2].record()
+        torch.cuda.synchronize()
+        best_sync, best_vit = min(best_sync, ev[0].elapsed_time(ev[1])), min(best_vit, ev[1].elapsed_time(ev[2]))
+    want = torch.from_numpy(frames).cuda().repeat(tiles, 1)
+    ok = (cadu[:, 4:] == want).all(dim=1) & (osc >= 53)
+    rec = {"symbols": int(nsym), "frames": int(nfr), "sync_ms": best_sync, "viterbi_ms": best_vit,
+           "sync_msym_s": nsym / best_sync / 1e3, "viterbi_msym_s": nsym / best_vit / 1e3,
+           "frontend_msym_s": nsym / (best_sync + best_vit) / 1e3,
+           "sync_hbm_gbs": nsym * 4.25 / (best_sync * 1e-3) / 1e9,
+           "frames_recovered_frac": float(ok.float().mean().item()),
+           "note": "soft stream resident in HBM; sync = pack + score (8 symmetries) + per-CADU peaks: 2 B read + 2.25 B written per "
+                   "symbol; Viterbi = one warp per CADU, 8320 add-compare-select steps + traceback"}
+    if rank == 0:
+        n_cpu = 1 << 20
+        t0 = time.perf_counter()
+        s_c, h_c = fe.sync_scores(block[:n_cpu])
+        t1 = time.perf_counter()
+        for f in range(8):
+            fe.viterbi_cadu(block, f * fe.CADU_SYMS, 1)
+        t2 = time.perf_counter()
+        rec["cpu_oracle_1core"] = {"sync_msym_s": n_cpu / (t1 - t0) / 1e6, "viterbi_msym_s": 8 * fe.CADU_SYMS / (t2 - t1) / 1e6}
+        same = bool(np.array_equal(score[:n_cpu].cpu().numpy(), s_c) and np.array_equal(hyp[:n_cpu].cpu().numpy(), h_c))
+        c0, _ = fe.viterbi_cadu(block, 3 * fe.CADU_SYMS, 1)
+        rec["equals_oracle"] = bool(same and np.array_equal(cadu[3].cpu().numpy(), c0))
+    return rec
 
 
 def bench_single_stream(cfg, local, rank, nsamples=1 << 22):

@@ -14,7 +14,9 @@
  *   - soft symbols leave in 512-symbol blocks, a block only if the PLL had locked once
  *     when it completed; the last partial block always   main.c:308-323
  *   - status line text                           main.c:253-258
- * What is not: the ncurses TUI (always batch-style status), the per-sample demod calls
+ * What is not: ncurses (the TUI panes of tui.c:139-247 -- input position, bytes out, lock / gain / carrier /
+ * symbol rate, constellation of the last 512 symbols -- are redrawn with plain ANSI escapes from the state
+ * snapshot taken after every block), the per-sample demod calls
  * (one lrpt_process call per input slab instead), and the final-flush length bug
  * (main.c:321 writes 2*ring_idx bytes, the second half stale or out of bounds) unless
  * --ref-compatible-tail asks for the reference's byte count.
@@ -26,6 +28,7 @@
 #include <getopt.h>
 #include <math.h>
 #include <poll.h>
+#include <pthread.h>
 #include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -43,7 +46,7 @@
 #define VERSION "1.0-b200"
 #endif
 
-enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD };
+enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD, OPT_TUI };
 
 static struct option longopts[] = {
 	{ "batch",        0, NULL, 'B' }, { "pll-bw",       1, NULL, 'b' },
@@ -55,6 +58,7 @@ static struct option longopts[] = {
 	{ "samplerate",   1, NULL, 's' }, { "bps",          1, NULL, 'S' },
 	{ "version",      0, NULL, 'v' }, { "device",       1, NULL, OPT_DEVICE },
 	{ "ref-compatible-tail", 0, NULL, OPT_REFTAIL }, { "shard", 1, NULL, OPT_SHARD },
+	{ "tui",          0, NULL, OPT_TUI },
 	{ NULL, 0, NULL, 0 }
 };
 
@@ -74,6 +78,7 @@ usage(const char *pname)
 	        "       --stdout            Write output symbols to stdout (implies -B, -q)\n"
 	        "       --device <n>        CUDA device ordinal (default: 0)\n"
 	        "       --ref-compatible-tail  Final flush writes the reference's byte count (main.c:321)\n"
+	        "       --tui               Full-screen status with constellation plot (default on a terminal without -B)\n"
 	        "       --shard <samples>   Offline speed-up for ONE long recording: cut it into chunks of <samples>\n"
 	        "                           (e.g. 256k) demodulated side by side on the GPU and joined; QPSK only;\n"
 	        "                           statistical parity (the first two chunks are exact), see DESIGN.md\n"
@@ -269,6 +274,133 @@ read_blocks(struct reader *r, uint8_t *dst, size_t want)
 	return whole;
 }
 
+/* ------------------------------------------------------------------ status panes ----
+ * The reference's interactive mode (main.c:222-245) redraws four ncurses panes every -R ms from the demodulator's
+ * statics and the symbol ring: tui_update_file_in, tui_update_data_out, tui_update_pll, tui_draw_constellation
+ * (tui.c:139-247). Here the same panes are fed from the snapshot lrpt_status returns after every block and from
+ * the last 512 symbols the host holds anyway (the egress ring), and drawn with ANSI escapes -- ncurses is not a
+ * dependency of this host. The constellation follows tui.c:165-201: cell (rows/2 - Q*rows/255, cols/2 + I*cols/255),
+ * density marks . - + # for 1, 2, 3, 4+ symbols in a cell, axes through the middle. */
+#define TUI_ROWS 21
+#define TUI_COLS 43
+
+static void
+seconds_to_str(char *dst, size_t n, unsigned long long secs)
+{
+	snprintf(dst, n, "%02llu:%02llu:%02llu", secs/3600, secs/60%60, secs%60);
+}
+
+static void
+tui_render(FILE *f, int ansi, const char *in_name, unsigned in_rate_bytes, unsigned long long done, unsigned long long total,
+           unsigned long long bytes_out, const lrpt_status_t *st, float freq_hz, float rate_hz,
+           const int8_t *dots, size_t ndots)
+{
+	static const char marks[] = " .-+#";
+	unsigned char grid[TUI_ROWS][TUI_COLS];
+	char t_done[32], t_total[32];
+	size_t i;
+	int r, c;
+	memset(grid, 0, sizeof(grid));
+	for (i = 0; i + 1 < 2*ndots; i += 2) {
+		const int x = dots[i]*TUI_COLS/255, y = dots[i + 1]*TUI_ROWS/255;
+		r = TUI_ROWS/2 - y; c = x + TUI_COLS/2;
+		if (r >= 0 && r < TUI_ROWS && c >= 0 && c < TUI_COLS && grid[r][c] < 4) grid[r][c]++;
+	}
+	seconds_to_str(t_done, sizeof(t_done), in_rate_bytes ? done/in_rate_bytes : 0);
+	seconds_to_str(t_total, sizeof(t_total), in_rate_bytes ? total/in_rate_bytes : 0);
+	if (ansi) fputs("\033[H\033[J", f);                     /* home, clear */
+	fprintf(f, "+- File in ------------------------------+\n");
+	fprintf(f, "  %s\n  %s / %s  (%5.1f%%)\n", in_name, t_done, t_total, total ? 100.0*done/total : 0.0);
+	fprintf(f, "+- Data out -----------------------------+\n");
+	fprintf(f, "  %llu bytes\n", bytes_out);
+	fprintf(f, "+- PLL ----------------------------------+\n");
+	fprintf(f, "  %s\n", st->locked ? "Locked" : "Acquiring...");
+	fprintf(f, "  Gain\tCarrier freq\tSymbol rate\n  %.3f\t%+7.1f Hz\t%7.1f Hz\n", st->agc_gain, freq_hz, rate_hz);
+	fprintf(f, "+- Constellation ------------------------+\n");
+	for (r = 0; r < TUI_ROWS; r++) {
+		fputs("  ", f);
+		for (c = 0; c < TUI_COLS; c++) {
+			char ch = marks[grid[r][c]];
+			if (ch == ' ') ch = (r == TUI_ROWS/2 && c == TUI_COLS/2) ? '+' : r == TUI_ROWS/2 ? '-' : c == TUI_COLS/2 ? '|' : ' ';
+			fputc(ch, f);
+		}
+		fputc('\n', f);
+	}
+	fflush(f);
+}
+
+/* ------------------------------------------------------------------ double-buffered ingest ----
+ * A reader thread fills one page-locked slab (read_blocks: whole 32 KiB blocks, live sources block by block)
+ * while the demodulator works on the other, so file / pipe reads overlap the GPU instead of alternating with it. */
+struct ingest {
+	struct reader rd;
+	uint8_t *slab[2];
+	size_t have[2], slab_bytes;
+	int filled[2], done;                                    /* filled[i]: slab i holds data the consumer has not taken */
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	pthread_t tid;
+};
+
+static void *
+ingest_thread(void *arg)
+{
+	struct ingest *g = arg;
+	int i = 0;
+	for (;;) {
+		pthread_mutex_lock(&g->mu);
+		while (g->filled[i]) pthread_cond_wait(&g->cv, &g->mu);
+		pthread_mutex_unlock(&g->mu);
+		const size_t n = read_blocks(&g->rd, g->slab[i], g->slab_bytes);
+		pthread_mutex_lock(&g->mu);
+		g->have[i] = n; g->filled[i] = 1;
+		if (!n || g->rd.eof) g->done = 1;
+		pthread_cond_broadcast(&g->cv);
+		pthread_mutex_unlock(&g->mu);
+		if (!n || g->rd.eof) return NULL;
+		i ^= 1;
+	}
+}
+
+/* next filled slab (blocks until the reader has one); 0 bytes = end of input */
+static size_t
+ingest_take(struct ingest *g, int i, uint8_t **data)
+{
+	pthread_mutex_lock(&g->mu);
+	while (!g->filled[i]) pthread_cond_wait(&g->cv, &g->mu);
+	pthread_mutex_unlock(&g->mu);
+	*data = g->slab[i];
+	return g->have[i];
+}
+
+/* hands slab i back to the reader; returns 1 when no further slab will come (the reader has stopped and the
+ * other slab holds nothing) */
+static int
+ingest_release(struct ingest *g, int i)
+{
+	int last;
+	pthread_mutex_lock(&g->mu);
+	last = g->done && !g->filled[i ^ 1];
+	g->filled[i] = 0;
+	pthread_cond_broadcast(&g->cv);
+	pthread_mutex_unlock(&g->mu);
+	return last;
+}
+
+static void *
+host_alloc(size_t n, int *pinned)
+{
+	void *p = lrpt_alloc_host(n);                          /* page-locked: the host link's full speed */
+	*pinned = p != NULL;
+	return p ? p : malloc(n);
+}
+
+static void
+host_free(void *p, int pinned)
+{
+	if (pinned) lrpt_free_host(p); else free(p);
+}
+
 /* Several recordings as the streams of one batch. All share the command line's settings and must agree
  * on sample rate and sample format; lengths may differ (a finished stream idles on silence, its output
  * is no longer written). Output of <input> goes to <input>.s. */
@@ -352,22 +484,44 @@ static int
 run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float symrate, int quiet, int ref_tail)
 {
 	size_t have = 0, room = (size_t)64 << 20;
-	uint8_t *raw = malloc(room);
+	int pinned = 0, pin_soft = 0;
+	uint8_t *raw = NULL;
 	struct reader *rd = calloc(1, sizeof(*rd));
 	if (!rd) { fprintf(stderr, "out of memory\n"); return 1; }
 	rd->in = in;
+	{
+		/* a seekable input's length is known: read it straight into ONE page-locked buffer (the H2D copy of a
+		 * 4.3 GB recording takes 80 ms from page-locked memory, 470 ms from malloc memory) */
+		const long pos = ftell(in);
+		if (pos >= 0 && !fseek(in, 0, SEEK_END)) {
+			const long end = ftell(in);
+			fseek(in, pos, SEEK_SET);
+			if (end > pos) {
+				room = (size_t)(end - pos) + FILE_BLOCK;
+				raw = lrpt_alloc_host(room);
+				pinned = raw != NULL;
+			}
+		}
+	}
+	if (!raw) raw = malloc(room);
 	while (raw && !rd->eof) {
-		if (room - have < (size_t)FILE_BLOCK*SLAB_BLOCKS) {
+		if (room - have < (size_t)FILE_BLOCK) {
+			if (pinned) break;                                  /* cannot happen: the buffer holds the whole file */
 			uint8_t *grown = realloc(raw, room *= 2);
 			if (!grown) { free(raw); raw = NULL; break; }
 			raw = grown;
 		}
-		have += read_blocks(rd, raw + have, (size_t)FILE_BLOCK*SLAB_BLOCKS);
+		size_t want = room - have;
+		if (want > (size_t)FILE_BLOCK*SLAB_BLOCKS) want = (size_t)FILE_BLOCK*SLAB_BLOCKS;
+		want = want/FILE_BLOCK*FILE_BLOCK;
+		const size_t got = read_blocks(rd, raw + have, want);
+		if (!got && !rd->eof) continue;
+		have += got;
 	}
 	if (!raw) { fprintf(stderr, "out of memory\n"); return 1; }
 	const size_t nsamples = have/((size_t)p->bps/4);
 	const size_t cap = (size_t)((double)nsamples*p->symrate/p->samplerate*1.02) + 64;
-	int8_t *soft = malloc(2*cap);
+	int8_t *soft = host_alloc(2*cap, &pin_soft);
 	if (!soft) { fprintf(stderr, "out of memory\n"); return 1; }
 	lrpt_shard_plan_t plan = { (chunk + 7)/8*8, 150000, 8192 };
 	lrpt_shard_report_t rep;
@@ -383,7 +537,8 @@ run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float sym
 		printf("(100.0%%) %zu samples in %d chunks, %zu symbols (%.1f Hz nominal), worst boundary agreement %.4f%s, Locked: %s\n",
 		       nsamples, rep.nchunks, nsym, symrate, rep.min_agreement_final, rep.aligned ? "" : " (a chunk kept another lock point)",
 		       rep.first_lock_symbol >= 0 ? "Yes" : "No");
-	free(raw); free(soft);
+	host_free(raw, pinned); host_free(soft, pin_soft);
+	free(rd);
 	return 0;
 }
 
@@ -392,7 +547,7 @@ main(int argc, char *argv[])
 {
 	float pll_bw = 1, symrate = 72000.0f, freq_max_delta = -1;
 	int rrc_order = 32, interp_factor = 5, quiet = 0, oqpsk = 0, batch = 0;
-	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0;
+	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0, tui = -1;
 	size_t shard = 0;
 	char *output_fname = NULL;
 	FILE *in, *out;
@@ -403,6 +558,7 @@ main(int argc, char *argv[])
 			case OPT_STDOUT: stdout_mode = 1; break;
 			case OPT_DEVICE: device = atoi(optarg); break;
 			case OPT_REFTAIL: ref_tail = 1; break;
+			case OPT_TUI: tui = 1; break;
 			case OPT_SHARD: shard = (size_t)human_to_float(optarg); break;
 			case 'b': pll_bw = human_to_float(optarg); break;
 			case 'B': batch = 1; break;
@@ -481,41 +637,60 @@ main(int argc, char *argv[])
 	const size_t bytes_per_sample = (size_t)bps/4;
 	const size_t slab_samples = slab_bytes/bytes_per_sample;
 	const size_t cap = slab_samples;                       /* a symbol needs at least one sample in any sane setup */
-	uint8_t *raw = malloc(slab_bytes);
-	int8_t *soft = malloc(2*cap);
+	int pin_soft = 0, pin_raw[2] = {0, 0};
+	int8_t *soft = host_alloc(2*cap, &pin_soft);
 	struct egress eg;
 	unsigned long long bytes_in = 0;
 	long long first_lock = -1;
 	double last_status = now_ms();
 	memset(&eg, 0, sizeof(eg));
 	eg.out = out;
-	if (!raw || !soft) { fprintf(stderr, "out of memory\n"); return 1; }
+	if (tui < 0) tui = !batch && !quiet && isatty(fileno(stdout));   /* main.c:222: interactive unless -B */
+	if (tui && out == stdout) tui = 0;
 
-	struct reader *rd = calloc(1, sizeof(*rd));
-	if (!rd) { fprintf(stderr, "out of memory\n"); return 1; }
-	rd->in = in;
-	for (;;) {
-		const size_t use = read_blocks(rd, raw, slab_bytes);
+	/* double-buffered ingest into page-locked slabs (reader thread) */
+	struct ingest *ing = calloc(1, sizeof(*ing));
+	if (!ing || !soft) { fprintf(stderr, "out of memory\n"); return 1; }
+	ing->rd.in = in;
+	ing->slab_bytes = slab_bytes;
+	ing->slab[0] = host_alloc(slab_bytes, &pin_raw[0]);
+	ing->slab[1] = host_alloc(slab_bytes, &pin_raw[1]);
+	if (!ing->slab[0] || !ing->slab[1]) { fprintf(stderr, "out of memory\n"); return 1; }
+	pthread_mutex_init(&ing->mu, NULL);
+	pthread_cond_init(&ing->cv, NULL);
+	if (pthread_create(&ing->tid, NULL, ingest_thread, ing)) { fprintf(stderr, "could not start the reader thread\n"); return 1; }
+	for (int cur = 0;; cur ^= 1) {
+		uint8_t *raw = NULL;
+		const size_t use = ingest_take(ing, cur, &raw);
 		if (!use) break;
 		size_t nsym = 0;
 		rc = lrpt_process(h, raw, use/bytes_per_sample, soft, cap, &nsym, &first_lock);
+		const int last = ingest_release(ing, cur);                  /* the reader stopped after this slab */
 		if (rc) { fprintf(stderr, "lrpt_process failed: %s (%s)\n", lrpt_strerror(rc), lrpt_last_error(h)); return 1; }
 		bytes_in += use;
 		egress_push(&eg, soft, nsym, first_lock);
 
-		if (!quiet && now_ms() - last_status >= update_interval) {
+		if (!quiet && (now_ms() - last_status >= update_interval || (tui && last))) {
 			lrpt_status_t st;
-			lrpt_status(h, 0, &st);
+			lrpt_status(h, 0, &st);                                  /* the snapshot after this block */
 			const float freq_hz = st.pll_freq*symrate/(2*M_PI)*(oqpsk ? 2 : 1);          /* main.c:250 */
 			const float rate_hz = st.mm_omega*(samplerate*interp_factor)/(2*M_PI);       /* main.c:251 */
-			printf(batch ? "\n" : "\033[1K\r");
-			printf("(%5.1f%%) Carrier: %+7.1f Hz, Symbol rate: %.1f Hz, Locked: %s",
-			       file_len ? 100.0*bytes_in/file_len : 0, freq_hz, rate_hz, st.locked ? "Yes" : "No");
-			fflush(stdout);
+			if (tui) {
+				/* the constellation ring: the last 512 symbols (main.c:34,243) = end of this block's output */
+				const size_t nd = nsym < RINGSIZE ? nsym : RINGSIZE;
+				tui_render(stdout, isatty(fileno(stdout)), argv[optind], 2*samplerate*bps/8, bytes_in, file_len, eg.bytes_out,
+				           &st, freq_hz, rate_hz, soft + 2*(nsym - nd), nd);
+			} else {
+				printf(batch ? "\n" : "\033[1K\r");
+				printf("(%5.1f%%) Carrier: %+7.1f Hz, Symbol rate: %.1f Hz, Locked: %s",
+				       file_len ? 100.0*bytes_in/file_len : 0, freq_hz, rate_hz, st.locked ? "Yes" : "No");
+				fflush(stdout);
+			}
 			last_status = now_ms();
 		}
-		if (rd->eof) break;
+		if (last) break;
 	}
+	pthread_join(ing->tid, NULL);
 
 	egress_finish(&eg, ref_tail);
 	if (!quiet) {
@@ -528,7 +703,8 @@ main(int argc, char *argv[])
 	}
 
 	lrpt_destroy(h);
-	free(raw); free(soft);
+	host_free(ing->slab[0], pin_raw[0]); host_free(ing->slab[1], pin_raw[1]); host_free(soft, pin_soft);
+	free(ing);
 	if (out != stdout) fclose(out);
 	if (in != stdin) fclose(in);
 	return 0;

@@ -234,6 +234,34 @@ typedef struct lrpt_shard_report {
 int  lrpt_sharded_process(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
                           int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep);
 
+/* ---- decoder front-end (csrc/frontend.cu) ----------------------------------------
+ * The consumer of this path's output in the reference's pipeline (README.md:6-9,87-91: the `.s` soft-symbol file
+ * or pipe goes to meteor_decode): frame synchronisation and Viterbi decoding of the int8 soft-symbol stream exactly
+ * as main.c:305-313 lays it out (I, Q per symbol, no header). The algorithm is the link layer's published one --
+ * CCSDS 131.0-B as Meteor-M LRPT uses it: ASM 0x1ACFFC1D, rate 1/2 K = 7 code, G1 = 171 (I) / G2 = 133 (Q), 8192
+ * symbols per 1024-byte CADU -- restated for the CPU in oracle/frontend_oracle.c, which these entry points
+ * reproduce bit for bit. Device buffers, asynchronous on `cuda_stream`, no handle.
+ *
+ * lrpt_fe_sync_device: per symbol offset o <= nsym - 32 the best match (0..64 equal bits) of the 64 hard
+ * decisions from o on with the encoded ASM under the 8 symmetries of the constellation, hyp = quarter turns
+ * (0..3) + 4 if I and Q are swapped (lowest on ties); later offsets get 0. d_score / d_hyp: nsym bytes rounded
+ * up to a multiple of 4; d_words: scratch of lrpt_fe_sync_words(nsym) uint32; d_soft 16-byte aligned.
+ * lrpt_fe_peaks_device: first offset of the highest score in every window of `window` offsets
+ * (ceil(nsym/window) results).
+ * lrpt_fe_viterbi_device: every frame f = the CADU starting at symbol d_frame_off[f] under symmetry
+ * d_frame_hyp[f] -> d_cadu[f*1024 .. +1024) (the first four bytes are the ASM when a frame really starts there)
+ * and the winning path metric; 64 symbols before and after the frame are decoded along with it. d_scratch:
+ * any multiple of 66560 bytes >= 4 of them (lrpt_fe_viterbi_scratch_bytes = enough for every SM). */
+int    lrpt_fe_sync_device(const int8_t *d_soft, size_t nsym, uint8_t *d_score, uint8_t *d_hyp, uint32_t *d_words,
+                           void *cuda_stream);
+size_t lrpt_fe_sync_words(size_t nsym);
+int    lrpt_fe_peaks_device(const uint8_t *d_score, const uint8_t *d_hyp, size_t nsym, uint32_t window, uint32_t *d_off,
+                            uint8_t *d_ohyp, uint8_t *d_oscore, void *cuda_stream);
+size_t lrpt_fe_viterbi_scratch_bytes(int device);
+int    lrpt_fe_viterbi_device(const int8_t *d_soft, size_t nsym, const uint32_t *d_frame_off, const uint8_t *d_frame_hyp,
+                              int nframes, uint8_t *d_cadu, int32_t *d_metric, void *d_scratch, size_t scratch_bytes,
+                              void *cuda_stream);
+
 /* ---- page-locked host buffers ---------------------------------------------------------------------
  * The host-buffer entry points (lrpt_process, lrpt_process_batch, lrpt_sharded_process) copy at the full
  * speed of the host link only from / to page-locked memory; from ordinary malloc memory the driver stages

@@ -82,6 +82,13 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrpt_sharded_process": (C.c_int, [C.POINTER(Params), C.POINTER(ShardPlan), C.c_void_p, C.c_size_t, C.c_void_p,
                                        C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(ShardReport)]),
+    "lrpt_fe_sync_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lrpt_fe_sync_words": (C.c_size_t, [C.c_size_t]),
+    "lrpt_fe_peaks_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "lrpt_fe_viterbi_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "lrpt_fe_viterbi_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "lrpt_alloc_host": (C.c_void_p, [C.c_size_t]),
     "lrpt_free_host": (None, [C.c_void_p]),
     "lrpt_pin_host": (C.c_int, [C.c_void_p, C.c_size_t]),

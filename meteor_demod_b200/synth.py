@@ -77,6 +77,23 @@ def baseband(nsamples, symrate=72000, fs=230000, oqpsk=False, seed=1, periodic=F
     return z / np.sqrt(np.mean(np.abs(z) ** 2))
 
 
+def modulate(symbols, symrate=72000, fs=230000, cfo_hz=700.0, phase=0.7, esn0_db=12.0, bps=16, rms=6000.0, seed=1):
+    """GIVEN complex QPSK symbols (+-1 +-1j, one per symbol period) -> raw I/Q as make_raw builds it: RRC pulse at 16x,
+    rational resampling to fs, unit rms, carrier offset + phase, AWGN, the raw sample format. For tests that need to
+    know what was sent (the decoder front-end behind the demodulator)."""
+    from scipy.signal import resample_poly
+
+    up, down = _ratio(fs, symrate)
+    sym = np.asarray(symbols, np.complex128)
+    x = np.zeros(sym.size * UP, np.complex128)
+    x[::UP] = sym
+    h = rrc_pulse()
+    y = np.convolve(x, h)[h.size // 2:][: x.size]
+    z = resample_poly(y, up, down)
+    z = z / np.sqrt(np.mean(np.abs(z) ** 2))
+    return to_raw(impair(z, fs, cfo_hz, phase, esn0_db, sps=fs / symrate, seed=seed + 1000), bps, rms)
+
+
 def impair(z, fs=230000, cfo_hz=700.0, phase=0.7, esn0_db=12.0, sps=None, seed=2, n0=0):
     """Carrier offset/phase + AWGN. Es/N0 refers to symbol energy: noise var = sps/EsN0 per sample."""
     n = np.arange(n0, n0 + z.size, dtype=np.float64)

@@ -183,3 +183,87 @@ def test_live_pipe_is_demodulated_as_it_arrives(host, oracle_mod, tmp_path):
     assert p.wait(timeout=60) == 0
     want, _ = expected(raw[44:], 8, oracle_mod, False, symrate=80000, oqpsk=1)
     assert out.read_bytes() == want
+
+
+def test_wav_variants_are_walked_chunk_by_chunk(host, oracle_mod, tmp_path):
+    """an 18-byte `fmt ` chunk and a `LIST` chunk before `data`. The reference takes any RIFF/WAVE
+    file for canonical (wavfile.c:34-49) and would demodulate the rest of such a header as samples; the host walks
+    the chunks and starts at the `data` payload: same bytes out as for the canonical file with the same samples."""
+    import struct
+    from meteor_demod_b200 import synth
+    raw = synth.make_raw(400_000, cfo_hz=40.0, seed=23).tobytes()
+    canon = tmp_path / "canon.wav"
+    canon.write_bytes(synth.wav_header(len(raw)) + raw)
+    fmt18 = struct.pack("<HHIIHHH", 1, 2, 230000, 230000 * 4, 4, 16, 0)
+    listck = b"LIST" + struct.pack("<I", 26) + b"INFOISFT" + struct.pack("<I", 14) + b"lrpt test file"
+    body = b"WAVE" + b"fmt " + struct.pack("<I", 18) + fmt18 + listck + b"data" + struct.pack("<I", len(raw)) + raw
+    ext = tmp_path / "ext.wav"
+    ext.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    a, b = tmp_path / "a.s", tmp_path / "b.s"
+    run([host, "-B", "-q", "-o", str(a), str(canon)])
+    run([host, "-B", "-q", "-o", str(b), str(ext)])
+    assert a.read_bytes() == b.read_bytes() and a.stat().st_size > 100_000
+    # the same file through a pipe (no seeking in the chunk walk)
+    c = tmp_path / "c.s"
+    run([host, "-B", "-q", "-o", str(c), "-"], stdin=ext.read_bytes())
+    assert c.read_bytes() == a.read_bytes()
+    # a mono file is not an I/Q recording: treated like the reference treats it (raw, needs -s)
+    mono = tmp_path / "mono.wav"
+    mono.write_bytes(synth.wav_header(len(raw), channels=1) + raw)
+    r = subprocess.run([host, "-B", "-q", "-o", str(tmp_path / "m.s"), str(mono)], capture_output=True)
+    assert r.returncode != 0 and b"sample rate" in r.stderr
+
+
+def test_status_panes(host, tmp_path):
+    """the interactive panes of tui.c:139-247 (input position, bytes out, lock / gain / carrier / symbol
+    rate, constellation of the last 512 symbols) from the per-block snapshots; --tui forces them onto a pipe (plain
+    text frames). The symbols written are the ones -B writes."""
+    from meteor_demod_b200 import synth
+    raw = synth.make_raw(1_200_000, cfo_hz=30.0, seed=24)
+    wav = tmp_path / "in.wav"
+    wav.write_bytes(synth.wav_header(raw.nbytes) + raw.tobytes())
+    a, b = tmp_path / "a.s", tmp_path / "b.s"
+    run([host, "-B", "-q", "-o", str(a), str(wav)])
+    r = run([host, "--tui", "-R", "0", "-o", str(b), str(wav)])
+    assert a.read_bytes() == b.read_bytes()
+    text = r.stdout.decode()
+    assert "File in" in text and "Data out" in text and "PLL" in text and "Constellation" in text
+    frame = text[text.rindex("+- File in"):]
+    assert "Locked" in frame and "Carrier freq" in frame and "00:00:05" in frame          # 1.2 M samples at 230 kS/s
+    plot = frame[frame.index("+- Constellation"):].splitlines()[1:22]
+    assert len(plot) == 21 and all(len(ln) <= 45 for ln in plot)
+    marks = sum(ln.count("#") + ln.count(".") for ln in plot)
+    assert marks > 20                                            # four clusters of a locked QPSK constellation
+    mid = plot[10]
+    assert "-" in mid and "|" in plot[2]                         # axes through the middle (iq_draw_quadrants)
+    # the clusters sit in the four quadrants, none on the axes' crossing
+    quad = [sum(ln[2:23].count("#") for ln in plot[:10]), sum(ln[24:].count("#") for ln in plot[:10]),
+            sum(ln[2:23].count("#") for ln in plot[11:]), sum(ln[24:].count("#") for ln in plot[11:])]
+    assert all(q > 0 for q in quad), quad
+
+
+def test_shard_reports_the_first_lock_of_a_late_signal(host, tmp_path):
+    """A recording that starts before the signal is up (the normal case for a satellite pass): chunk 0 sees only
+    noise and never locks, so --shard must take the stream-wide first lock from the later chunks instead of
+    dropping every block (main.c:312 gates the output on pll_did_lock_once()). The instant itself is Tier-S: every
+    chunk runs the reference's acquisition sweep (pll.c:126) from its own start, so it finds a carrier at +700 Hz
+    sooner than the sequential run, whose sweep has passed that frequency while it was still listening to noise."""
+    from meteor_demod_b200 import sharded, synth
+    rng = np.random.default_rng(5)
+    n_noise, n_sig = 450_000, 1_800_000
+    noise = np.clip(np.rint(rng.normal(0, 1500, 2 * n_noise)), -32768, 32767).astype(np.int16)
+    sig = synth.make_raw(n_sig, cfo_hz=700.0, seed=25)
+    raw = np.concatenate([noise, sig])
+    got, rep = sharded.process_host(raw, chunk=262144, warm=150000, overlap=8192)
+    sym_per_sample = 72000 / 230000
+    assert rep["nchunks"] >= 8
+    assert rep["first_lock_symbol"] >= int(0.95 * n_noise * sym_per_sample), rep       # not on noise
+    assert rep["first_lock_symbol"] <= int((n_noise + 700_000) * sym_per_sample), rep   # within two chunks of the signal
+    wav = tmp_path / "late.wav"
+    wav.write_bytes(synth.wav_header(raw.nbytes) + raw.tobytes())
+    out = tmp_path / "late.s"
+    run([host, "-B", "-q", "--shard", "262144", "-o", str(out), str(wav)])
+    nbytes = out.stat().st_size
+    nsym = int((raw.size // 2 // 8192 * 8192) * sym_per_sample)
+    assert nbytes >= 2 * (nsym - rep["first_lock_symbol"] - 2048), (nbytes, nsym, rep)   # everything from the lock block on
+    assert nbytes <= 2 * (nsym - int(0.9 * n_noise * sym_per_sample) + 2048)
