@@ -82,7 +82,7 @@ def test_gpu_viterbi_equals_oracle(lib, oracle_mod):
     import torch
     from meteor_demod_b200 import frontend
     from oracle import pyfrontend as fe
-    frames, soft = frames_and_stream(n=5, lead=777, noise=70.0, turns=2, swap=True, seed=30)
+    frames, soft = frames_and_stream(n=5, lead=777, noise=52.0, turns=2, swap=True, seed=30)
     nsym = soft.shape[0]
     offs = [777 + f * fe.CADU_SYMS for f in range(5)] + [0, 5, 700, 777 + 3, nsym - 8192, nsym - 4000, nsym - 10]
     hyps = [6] * 5 + [6, 0, 3, 6, 6, 1, 7]
@@ -97,7 +97,7 @@ def test_gpu_viterbi_equals_oracle(lib, oracle_mod):
         assert int(metric[k]) == wm, (k, o, h)
         if k < 5:
             errors += int(np.unpackbits(want[4:] ^ frames[k]).sum())
-    assert 0 < errors < 2000                                   # the channel is bad enough to exercise ties and wrong paths
+    assert 0 < errors < 4000                                   # the channel is bad enough to exercise ties and wrong paths
     # many frames: more frames than resident warps, decoded in several rounds
     reps = torch.tensor(offs[:5] * 400, dtype=torch.int32, device="cuda")
     many, _ = vit.decode(d_soft, reps, torch.full((2000,), 6, dtype=torch.uint8, device="cuda"))
