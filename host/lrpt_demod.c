@@ -46,7 +46,7 @@
 #define VERSION "1.0-b200"
 #endif
 
-enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD, OPT_TUI };
+enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD, OPT_TUI, OPT_GPUS };
 
 static struct option longopts[] = {
 	{ "batch",        0, NULL, 'B' }, { "pll-bw",       1, NULL, 'b' },
@@ -58,7 +58,7 @@ static struct option longopts[] = {
 	{ "samplerate",   1, NULL, 's' }, { "bps",          1, NULL, 'S' },
 	{ "version",      0, NULL, 'v' }, { "device",       1, NULL, OPT_DEVICE },
 	{ "ref-compatible-tail", 0, NULL, OPT_REFTAIL }, { "shard", 1, NULL, OPT_SHARD },
-	{ "tui",          0, NULL, OPT_TUI },
+	{ "tui",          0, NULL, OPT_TUI },          { "gpus",         1, NULL, OPT_GPUS },
 	{ NULL, 0, NULL, 0 }
 };
 
@@ -82,6 +82,8 @@ usage(const char *pname)
 	        "       --shard <samples>   Offline speed-up for ONE long recording: cut it into chunks of <samples>\n"
 	        "                           (e.g. 256k) demodulated side by side on the GPU and joined; QPSK only;\n"
 	        "                           statistical parity (the first two chunks are exact), see DESIGN.md\n"
+	        "       --gpus <n>          With --shard: spread the chunks over CUDA devices <device> .. <device>+n-1 (state and\n"
+	        "                           overlap symbols of the boundary chunks travel over NCCL); same bytes as one GPU\n"
 	        "   Several input files are demodulated together as one batch; output goes to <file_in>.s each\n"
 	        "\n"
 	        "   -h, --help              Print this help screen\n"
@@ -481,7 +483,7 @@ run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps
 /* --shard: the whole recording (whole 32 KiB blocks of it, wavfile.c:55) in memory, one lrpt_sharded_process
  * call, then the reference's egress rules (main.c:305-323) on the joined symbols. */
 static int
-run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float symrate, int quiet, int ref_tail)
+run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float symrate, int quiet, int ref_tail, int gpus)
 {
 	size_t have = 0, room = (size_t)64 << 20;
 	int pinned = 0, pin_soft = 0;
@@ -526,7 +528,12 @@ run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float sym
 	lrpt_shard_plan_t plan = { (chunk + 7)/8*8, 150000, 8192 };
 	lrpt_shard_report_t rep;
 	size_t nsym = 0;
-	int rc = lrpt_sharded_process(p, &plan, raw, nsamples, soft, cap, &nsym, &rep);
+	int rc, devs[64], g;
+	if (gpus < 1) gpus = 1;
+	if (gpus > 64) gpus = 64;
+	for (g = 0; g < gpus; g++) devs[g] = p->device + g;
+	rc = gpus > 1 ? lrpt_sharded_process_multi(p, &plan, raw, nsamples, soft, cap, &nsym, &rep, devs, gpus)
+	              : lrpt_sharded_process(p, &plan, raw, nsamples, soft, cap, &nsym, &rep);
 	if (rc) { fprintf(stderr, "lrpt_sharded_process failed: %s\n", lrpt_strerror(rc)); return 1; }
 	struct egress eg;
 	memset(&eg, 0, sizeof(eg));
@@ -547,7 +554,7 @@ main(int argc, char *argv[])
 {
 	float pll_bw = 1, symrate = 72000.0f, freq_max_delta = -1;
 	int rrc_order = 32, interp_factor = 5, quiet = 0, oqpsk = 0, batch = 0;
-	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0, tui = -1;
+	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0, tui = -1, gpus = 1;
 	size_t shard = 0;
 	char *output_fname = NULL;
 	FILE *in, *out;
@@ -559,6 +566,7 @@ main(int argc, char *argv[])
 			case OPT_DEVICE: device = atoi(optarg); break;
 			case OPT_REFTAIL: ref_tail = 1; break;
 			case OPT_TUI: tui = 1; break;
+			case OPT_GPUS: gpus = atoi(optarg); break;
 			case OPT_SHARD: shard = (size_t)human_to_float(optarg); break;
 			case 'b': pll_bw = human_to_float(optarg); break;
 			case 'B': batch = 1; break;
@@ -617,7 +625,7 @@ main(int argc, char *argv[])
 	p.device = device; p.nstreams = 1; p.kernel = LRPT_KERNEL_AUTO;
 	if (shard) {
 		if (!quiet) printf("Input: %s, output: %s\n", argv[optind], output_fname);
-		int src = run_sharded(in, out, &p, shard, symrate, quiet, ref_tail);
+		int src = run_sharded(in, out, &p, shard, symrate, quiet, ref_tail, gpus);
 		if (out != stdout) fclose(out);
 		if (in != stdin) fclose(in);
 		return src;

@@ -233,6 +233,18 @@ typedef struct lrpt_shard_report {
 } lrpt_shard_report_t;
 int  lrpt_sharded_process(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
                           int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep);
+/*
+ * The same over `ndev` GPUs of one node, driven from this one process (one host thread per device, no Python):
+ * device i takes a consecutive run of chunks and only its time slice of the recording (+ the warm-up and overlap
+ * it over-reads). What crosses a device boundary is the reference's state vector of the boundary chunk
+ * (lrpt_state_t + delay line: pll.c:16-20,112, timing.c:13-14,43, agc.c:9-10, filter.h:5-11, demod.c:54) and that
+ * chunk's overlap symbols for the quadrant scan, by ncclSend / ncclRecv (NCCL is loaded at run time, libnccl.so.2);
+ * quarter-turn sums and symbol counts are integers in host memory. Byte-identical to lrpt_sharded_process.
+ * devices: CUDA ordinals (p->device is ignored when ndev > 1); fewer devices are used when the recording has fewer
+ * than two chunks per device. rep->launches is per device.
+ */
+int  lrpt_sharded_process_multi(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
+                                int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep, const int *devices, int ndev);
 
 /* ---- decoder front-end (csrc/frontend.cu) ----------------------------------------
  * The consumer of this path's output in the reference's pipeline (README.md:6-9,87-91: the `.s` soft-symbol file

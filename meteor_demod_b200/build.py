@@ -52,7 +52,7 @@ def build(verbose=False, force=False):
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
     if force or _stale(SO, objs):
-        cmd = [NVCC, "-shared", "-o", SO] + objs + ["-cudart", "static", "-lm"]
+        cmd = [NVCC, "-shared", "-o", SO] + objs + ["-cudart", "static", "-lm", "-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

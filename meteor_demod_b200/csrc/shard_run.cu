@@ -1,8 +1,8 @@
 /*
- * shard_run.cu -- ONE recording, time-sharded over the lanes of one GPU, behind a single C call
- * (lrpt_sharded_process): what meteor_demod_b200/sharded.py::run_handoff does, for hosts without
- * Python (host/lrpt_demod --shards). A client of the public ABI only: the chunks run as the streams
- * of an ordinary batch handle, the join is csrc/shard_stitch.cu.
+ * shard_run.cu -- ONE recording, time-sharded over the lanes of one GPU or of several, behind a single C call
+ * (lrpt_sharded_process / lrpt_sharded_process_multi): what meteor_demod_b200/sharded.py::run_handoff does, for
+ * hosts without Python (host/lrpt_demod --shard [--gpus N]). A client of the public ABI only: the chunks run as
+ * the streams of ordinary batch handles (one per GPU), the join is csrc/shard_stitch.cu.
  *
  * The reference demodulates a recording as one sequential recurrence (demod.c:24-48, main.c:303-317);
  * its result cannot be reproduced bit for bit by anything that starts in the middle (DESIGN.md section
@@ -19,15 +19,25 @@
  *   pass C  every chunk again, C + V samples from B_c + V, now on a trajectory with W + C + V samples
  *           of history at the sequential run's lock point; chunk 1 continues chunk 0 exactly
  *   join    cut points mid-way between symbols, runs gathered in stream order
+ *
+ * Several GPUs (one host thread per device = "rank", consecutive runs of chunks, every rank holding only its time
+ * slice of the recording plus the warm-up and overlap it over-reads): what crosses a rank boundary is exactly the
+ * reference's state vector (pll.c:16-20,112, timing.c:13-14,43, agc.c:9-10, filter.h:5-11,
+ * demod.c:54) of the rank's last chunk -- lrpt_export_states_device bytes, by ncclSend / ncclRecv over NVLink --
+ * and that chunk's overlap symbols for the quadrant scan and the cut, also by ncclSend / ncclRecv; the quarter-turn
+ * prefix and the symbol counts are integers the threads share in host memory. NCCL is loaded at run time
+ * (libnccl.so.2) and only when more than one device is asked for. The result is byte-identical to the one-GPU run.
  */
 #include <cuda_runtime.h>
-#include <chrono>
+#include <dlfcn.h>
 #include <limits.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <vector>
 #include "lrpt_b200.h"
 
@@ -36,7 +46,7 @@ namespace {
 struct DevBuf {
 	void *p = nullptr;
 	~DevBuf() { if (p) cudaFree(p); }
-	cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+	cudaError_t alloc(size_t n) { if (p) { cudaFree(p); p = nullptr; } return cudaMalloc(&p, n ? n : 1); }
 	template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
@@ -52,8 +62,9 @@ size_t symbol_capacity(size_t nsamples, const lrpt_params_t &p)
 
 /* LRPT_SHARD_TIMING=1: wall time of every phase on stderr (device work is synchronised at each mark) */
 struct Phases {
-	bool on = getenv("LRPT_SHARD_TIMING") != nullptr;
+	bool on;
 	std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+	explicit Phases(bool enable) : on(enable && getenv("LRPT_SHARD_TIMING") != nullptr) {}
 	void mark(const char *what)
 	{
 		if (!on) return;
@@ -96,17 +107,413 @@ int scan_rows(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, siz
 	return LRPT_OK;
 }
 
+/* ------------------------------------------------------------------ NCCL, loaded at run time ---- */
+
+typedef struct ncclComm *ncclComm_t;
+struct Nccl {
+	void *lib = nullptr;
+	int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+	int (*CommDestroy)(ncclComm_t) = nullptr;
+	int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*GroupStart)(void) = nullptr;
+	int (*GroupEnd)(void) = nullptr;
+	bool load()
+	{
+		lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib) return false;
+#define SYM(field, name) *(void **)(&field) = dlsym(lib, name)
+		SYM(CommInitAll, "ncclCommInitAll"); SYM(CommDestroy, "ncclCommDestroy"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+		SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd");
+#undef SYM
+		return CommInitAll && CommDestroy && Send && Recv && GroupStart && GroupEnd;
+	}
+};
+constexpr int NCCL_CHAR = 0;                                    /* ncclInt8 / ncclChar */
+
+/* What the rank threads share (host memory): integers only. */
+struct Shared {
+	int world = 1;
+	pthread_barrier_t bar;
+	std::vector<int> rc, ksum, ksum2, aligned, launches;
+	std::vector<float> agree_scan, agree_final;
+	std::vector<long long> nsym_rank, first_lock_rank;          /* symbols a rank contributes; its first locked output symbol (-1) */
+	long long head_lock = -1;                                   /* chunk 0's own first lock (exact) */
+	Nccl *nccl = nullptr;
+	std::vector<ncclComm_t> comms;
+	bool failed() const { for (int v : rc) if (v) return true; return false; }
+};
+
+struct Job {
+	const lrpt_params_t *params; const lrpt_shard_plan_t *plan;
+	const uint8_t *raw; size_t nsamples;
+	int8_t *soft; size_t cap;
+	size_t M;                                                   /* chunks in the whole stream */
+};
+
+void split_rows(size_t M, int world, int rank, size_t &c0, size_t &c1)
+{
+	const size_t base = M/(size_t)world, extra = M%(size_t)world;
+	c0 = (size_t)rank*base + ((size_t)rank < extra ? (size_t)rank : extra);
+	c1 = c0 + base + ((size_t)rank < extra ? 1 : 0);
+}
+
+/* One rank: rows [c0, c1) of the stream on device `dev`. Every rank walks the same sequence of barriers and
+ * NCCL exchanges; an error is recorded and the walk goes on with whatever it has, so nobody waits for ever. */
+struct Rank {
+	Job job; Shared *sh; int rank, dev;
+	cudaStream_t st = nullptr;
+
+	int xfer(const void *send, void *recv, size_t bytes)        /* my buffer -> next rank, previous rank -> my buffer */
+	{
+		if (sh->world < 2) return LRPT_OK;
+		Nccl &n = *sh->nccl;
+		int e = n.GroupStart();
+		if (!e && send && rank + 1 < sh->world) e = n.Send(send, bytes, NCCL_CHAR, rank + 1, sh->comms[rank], st);
+		if (!e && recv && rank > 0) e = n.Recv(recv, bytes, NCCL_CHAR, rank - 1, sh->comms[rank], st);
+		const int e2 = n.GroupEnd();
+		if (e || e2) return LRPT_ERR_CUDA;
+		CK(cudaStreamSynchronize(st));
+		return LRPT_OK;
+	}
+	void sync() { pthread_barrier_wait(&sh->bar); }
+
+	int run()
+	{
+		const lrpt_params_t &params = *job.params;
+		const size_t C = job.plan->chunk, W = job.plan->warm, V = job.plan->overlap, nsamples = job.nsamples;
+		const size_t bytes = (size_t)params.bps/4;
+		const long long L = params.interp_factor;
+		const int world = sh->world;
+		size_t c0, c1;
+		split_rows(job.M, world, rank, c0, c1);
+		const size_t M = c1 - c0;
+		const bool first = rank == 0, last = rank == world - 1;
+		int rc = LRPT_OK;
+		Phases ph(first);
+		auto fail = [&](int code) { if (!rc) rc = code; sh->rc[rank] = rc; };
+#define TRY(x) do { if (!rc) { const int rc_ = (x); if (rc_) fail(rc_); } } while (0)
+#define TRYCU(x) do { if (!rc && (x) != cudaSuccess) fail(LRPT_ERR_CUDA); } while (0)
+
+		TRYCU(cudaSetDevice(dev));
+		TRYCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		lrpt_params_t p = params;
+		p.nstreams = (int32_t)M; p.device = dev;
+		Handle hd;
+		TRY(lrpt_create(&hd.h, &p));
+		lrpt_demod_t *h = hd.h;
+
+		/* this rank's time slice on its device: samples [c0*C, (c1-1)*C + W + C + 2V), zero padded behind the stream */
+		const size_t s0 = c0*C, span = (M - 1)*C + W + C + 2*V;
+		const size_t have = s0 < nsamples ? (nsamples - s0 < span ? nsamples - s0 : span) : 0;
+		const size_t n_row = C + V;
+		const size_t cap_row = (symbol_capacity(W > n_row ? W : n_row, p) + 7)/8*8;
+		const size_t soft_stride = 2*cap_row, q_stride = 4*cap_row;
+		DevBuf d_raw, d_soft, d_q, d_nsym, d_cnt, d_base, d_states, d_pack, d_two_soft, d_two_q, d_two_cnt, d_two_base, d_st_io;
+		TRYCU(d_raw.alloc(span*bytes)); TRYCU(d_soft.alloc(M*soft_stride)); TRYCU(d_q.alloc(M*q_stride)); TRYCU(d_nsym.alloc(4*M));
+		TRYCU(d_cnt.alloc(4*M)); TRYCU(d_base.alloc(8*M));
+		/* a boundary row on its way to the next rank: symbols, sub-step indices, then count (int32) and base (int64) */
+		const size_t pack_bytes = soft_stride + q_stride + 16;
+		TRYCU(d_pack.alloc(2*pack_bytes));                          /* [0]: outgoing, [1]: incoming */
+		TRYCU(d_two_soft.alloc(2*soft_stride)); TRYCU(d_two_q.alloc(2*q_stride)); TRYCU(d_two_cnt.alloc(8)); TRYCU(d_two_base.alloc(16));
+		ph.mark("handle + device buffers");
+		if (!rc && have < span) TRYCU(cudaMemsetAsync(d_raw.as<char>() + have*bytes, 0, (span - have)*bytes, st));
+		if (!rc && have) TRYCU(cudaMemcpyAsync(d_raw.p, job.raw + s0*bytes, have*bytes, cudaMemcpyHostToDevice, st));
+		TRYCU(cudaStreamSynchronize(st));
+		ph.mark("H2D of the recording");
+		if (h) TRY(lrpt_set_symbol_index_output(h, d_q.as<uint32_t>(), q_stride));
+		const char *raw0 = d_raw.as<char>();
+		std::vector<uint32_t> counts(M, 0);
+		std::vector<int64_t> base(M, 0);
+		auto run_pass = [&](size_t first_sample, size_t n) {        /* first_sample: offset within every row's own span */
+			if (h) TRY(lrpt_process_batch_device(h, raw0 + first_sample*bytes, C*bytes, n, d_soft.as<int8_t>(), soft_stride, cap_row,
+			                                     d_nsym.as<uint32_t>(), nullptr, 0, nullptr));
+			if (h) TRY(lrpt_sync(h, nullptr));
+			if (h) TRY(lrpt_get_counts(h, counts.data(), (int)M));
+			for (size_t c = 0; c < M && !rc; c++) if (counts[c] > cap_row) fail(LRPT_ERR_CAP);   /* the stitch kernels trust the counts */
+			for (size_t c = 0; c < M; c++) base[c] = (long long)((c0 + c)*C + first_sample)*L;
+			TRYCU(cudaMemcpy(d_cnt.p, counts.data(), 4*M, cudaMemcpyHostToDevice));   /* uint32 counts < 2^31: read as int32 */
+			TRYCU(cudaMemcpy(d_base.p, base.data(), 8*M, cudaMemcpyHostToDevice));
+		};
+		auto cut_target = [&](size_t c, size_t shift) { return (long long)(W + c*C + shift + (V/4 < 64 ? V/4 : 64))*L; };
+
+		/* my last row -> the next rank, the previous rank's last row -> rows (prev | my first) as a two-row problem.
+		 * Returns k, agreement and cut of the boundary in front of my first row (rank > 0). */
+		auto boundary_with_prev = [&](size_t shift, int32_t &k_prev, float &agree_prev, int64_t &cut_prev) {
+			k_prev = 0; agree_prev = 1.0f; cut_prev = -1;
+			if (world < 2) return;
+			char *out = d_pack.as<char>(), *in = out + pack_bytes;
+			if (!rc && !last) {
+				const size_t r = M - 1;
+				TRYCU(cudaMemcpyAsync(out, d_soft.as<char>() + r*soft_stride, soft_stride, cudaMemcpyDeviceToDevice, st));
+				TRYCU(cudaMemcpyAsync(out + soft_stride, d_q.as<char>() + r*q_stride, q_stride, cudaMemcpyDeviceToDevice, st));
+				TRYCU(cudaMemcpyAsync(out + soft_stride + q_stride, d_cnt.as<char>() + 4*r, 4, cudaMemcpyDeviceToDevice, st));
+				TRYCU(cudaMemcpyAsync(out + soft_stride + q_stride + 8, d_base.as<char>() + 8*r, 8, cudaMemcpyDeviceToDevice, st));
+			}
+			const int e = xfer(last ? nullptr : out, first ? nullptr : in, pack_bytes);   /* always entered: the peers wait for it */
+			if (e) fail(e);
+			if (first || rc) return;
+			TRYCU(cudaMemcpyAsync(d_two_soft.p, in, soft_stride, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_soft.as<char>() + soft_stride, d_soft.p, soft_stride, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_q.p, in + soft_stride, q_stride, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_q.as<char>() + q_stride, d_q.p, q_stride, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_cnt.p, in + soft_stride + q_stride, 4, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_cnt.as<char>() + 4, d_cnt.p, 4, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_base.p, in + soft_stride + q_stride + 8, 8, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaMemcpyAsync(d_two_base.as<char>() + 8, d_base.p, 8, cudaMemcpyDeviceToDevice, st));
+			TRYCU(cudaStreamSynchronize(st));
+			std::vector<int64_t> tgt(1, cut_target(c0, shift)), cut;
+			std::vector<int32_t> k;
+			std::vector<float> ag;
+			TRY(scan_rows(d_two_soft.as<int8_t>(), soft_stride, d_two_q.as<uint32_t>(), q_stride, d_two_cnt.as<int32_t>(),
+			              d_two_base.as<int64_t>(), 2, tgt, k, ag, cut));
+			if (!rc) { k_prev = k[0]; agree_prev = ag[0]; cut_prev = cut[0]; }
+		};
+
+		/* ---- pass A: warm-up; chunk 0's warm-up symbols open the output (they are the sequential run's) ---- */
+		std::vector<int8_t> head;                                   /* rank 0: chunk 0's own symbols (passes A and B) */
+		if (W) {
+			run_pass(0, W);
+			if (first && !rc) {
+				head.resize(2*(size_t)counts[0]);
+				TRYCU(cudaMemcpy(head.data(), d_soft.p, head.size(), cudaMemcpyDeviceToHost));
+			}
+		}
+		ph.mark("pass A (warm-up)");
+		/* ---- pass B: owned + overlap, from the live state ---- */
+		run_pass(W, n_row);
+		ph.mark("pass B");
+		std::vector<int64_t> target(M > 1 ? M - 1 : 0), cut;
+		std::vector<int32_t> k;
+		std::vector<float> agree;
+		for (size_t c = 1; c < M; c++) target[c - 1] = cut_target(c0 + c, 0);
+		TRY(scan_rows(d_soft.as<int8_t>(), soft_stride, d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), (int)M,
+		              target, k, agree, cut));
+		if (rc) { k.assign(M > 1 ? M - 1 : 0, 0); agree.assign(k.size(), 0.0f); }
+		int32_t k_prev = 0; float agree_prev = 1.0f; int64_t cut_prev = -1;
+		boundary_with_prev(0, k_prev, agree_prev, cut_prev);
+		float min_scan = agree_prev;
+		for (float a : agree) min_scan = a < min_scan ? a : min_scan;
+		sh->agree_scan[rank] = min_scan;
+		{
+			int s = k_prev;
+			for (int32_t v : k) s += v;
+			sh->ksum[rank] = s & 3;
+		}
+		sync();                                                     /* everybody's quarter-turn sums are in */
+		std::vector<int32_t> K(M, 0);
+		{
+			int kf = k_prev;
+			for (int j = 0; j < rank; j++) kf += sh->ksum[j];
+			K[0] = kf & 3;
+			for (size_t c = 1; c < M; c++) K[c] = (K[c - 1] + k[c - 1]) & 3;
+		}
+		if (first && !rc) {
+			/* chunk 0's pass-B symbols continue the head, up to the end of the stream */
+			DevBuf lo, hi, stt, ln;
+			const int64_t l = -1, hh = (int64_t)nsamples*L - 1;
+			int32_t s_0 = 0, n_0 = 0;
+			TRYCU(lo.alloc(8)); TRYCU(hi.alloc(8)); TRYCU(stt.alloc(4)); TRYCU(ln.alloc(4));
+			TRYCU(cudaMemcpy(lo.p, &l, 8, cudaMemcpyHostToDevice)); TRYCU(cudaMemcpy(hi.p, &hh, 8, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_ranges_device(d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), 1, lo.as<int64_t>(),
+			                             hi.as<int64_t>(), stt.as<int32_t>(), ln.as<int32_t>(), nullptr));
+			TRYCU(cudaMemcpy(&s_0, stt.p, 4, cudaMemcpyDeviceToHost)); TRYCU(cudaMemcpy(&n_0, ln.p, 4, cudaMemcpyDeviceToHost));
+			if (!rc) {
+				const size_t at = head.size();
+				head.resize(at + 2*(size_t)n_0);
+				TRYCU(cudaMemcpy(head.data() + at, d_soft.as<int8_t>() + 2*(size_t)s_0, 2*(size_t)n_0, cudaMemcpyDeviceToHost));
+			}
+			lrpt_status_t s;
+			memset(&s, 0, sizeof(s));
+			s.first_lock_symbol = -1;
+			if (h) TRY(lrpt_status(h, 0, &s));
+			if (!rc) sh->head_lock = s.first_lock_symbol;            /* chunk 0 counts its symbols as the stream does */
+		}
+		ph.mark("quadrant scan + chunk 0");
+
+		/* ---- hand-off: row c starts pass C from row c-1's end state, its Costas NCO turned back K[c-1] quarter turns
+		 * (p_phase = (float)((double)p_phase - K*pi/2), as lrpt_restore does; pll.c:16); across a rank boundary that
+		 * one state travels by ncclSend / ncclRecv ---- */
+		std::vector<long long> nsym_start(M, 0);                    /* symbol count row c inherits at the start of pass C */
+		{
+			const size_t total = h ? lrpt_states_size(h) : 0, sb = sizeof(lrpt_state_t);
+			const size_t hb = M && total ? (total - M*sb)/M : 0;    /* delay line bytes per row */
+			const size_t one = sb + hb;
+			TRYCU(d_states.alloc(total)); TRYCU(d_st_io.alloc(2*one));
+			if (h) TRY(lrpt_export_states_device(h, d_states.p, total, nullptr));
+			if (h) TRY(lrpt_sync(h, nullptr));
+			std::vector<char> cur(total), nxt(total), io(2*one);
+			TRYCU(cudaMemcpy(cur.data(), d_states.p, total, cudaMemcpyDeviceToHost));
+			lrpt_state_t *sc = reinterpret_cast<lrpt_state_t *>(cur.data()), *sn = reinterpret_cast<lrpt_state_t *>(nxt.data());
+			if (!rc) {
+				for (size_t c = 0; c < M; c++)
+					sc[c].p_phase = (float)((double)sc[c].p_phase - (double)(K[c] & 3)*1.57079632679489661923);
+				memcpy(io.data(), &sc[M - 1], sb);                  /* my last row's turned state -> the next rank */
+				memcpy(io.data() + sb, cur.data() + M*sb + (M - 1)*hb, hb);
+				TRYCU(cudaMemcpy(d_st_io.p, io.data(), one, cudaMemcpyHostToDevice));
+				TRYCU(cudaDeviceSynchronize());
+			}
+			const int e = xfer(last ? nullptr : d_st_io.p, first ? nullptr : d_st_io.as<char>() + one, one);
+			if (e) fail(e);
+			if (!rc) {
+				if (!first) {
+					TRYCU(cudaMemcpy(io.data() + one, d_st_io.as<char>() + one, one, cudaMemcpyDeviceToHost));
+					memcpy(&sn[0], io.data() + one, sb);
+					memcpy(nxt.data() + M*sb, io.data() + one + sb, hb);
+				} else {
+					sn[0] = sc[0];                                  /* chunk 0 has no predecessor; its pass C is not used */
+					memcpy(nxt.data() + M*sb, cur.data() + M*sb, hb);
+				}
+				for (size_t c = 1; c < M; c++) {
+					sn[c] = sc[c - 1];
+					memcpy(nxt.data() + M*sb + c*hb, cur.data() + M*sb + (c - 1)*hb, hb);
+				}
+				for (size_t c = 0; c < M; c++) nsym_start[c] = sn[c].nsymbols;
+				TRYCU(cudaMemcpy(d_states.p, nxt.data(), total, cudaMemcpyHostToDevice));
+				TRYCU(cudaDeviceSynchronize());                     /* pageable upload on the legacy stream: not ordered with the handle's stream */
+				TRY(lrpt_import_states_device(h, d_states.p, total, 1, nullptr));
+				TRY(lrpt_sync(h, nullptr));
+			}
+		}
+		ph.mark("state hand-off");
+
+		/* ---- pass C, then the join. Rank 0: rows 0 and 1 are one exact trajectory, so its table is rows 1.. with
+		 * nothing cut off the front of row 1; other ranks: all their rows, the first one cut against the previous rank's last ---- */
+		run_pass(W + V, n_row);
+		ph.mark("pass C");
+		const size_t skip = first ? 1 : 0;
+		const int n = (int)(M - skip);
+		const int8_t *soft1 = d_soft.as<int8_t>() + skip*soft_stride;
+		const uint32_t *q1 = reinterpret_cast<const uint32_t *>(d_q.as<char>() + skip*q_stride);
+		const int32_t *cnt1 = d_cnt.as<int32_t>() + skip;
+		const int64_t *base1 = d_base.as<int64_t>() + skip;
+		std::vector<int64_t> target2(n > 1 ? n - 1 : 0), cut2;
+		std::vector<int32_t> k2;
+		std::vector<float> agree2;
+		for (int b = 0; b + 1 < n; b++) target2[b] = cut_target(c0 + skip + (size_t)b + 1, V);
+		TRY(scan_rows(soft1, soft_stride, q1, q_stride, cnt1, base1, n, target2, k2, agree2, cut2));
+		if (rc) { k2.assign(n > 1 ? n - 1 : 0, 0); agree2.assign(k2.size(), 0.0f); cut2.assign(k2.size(), 0); }
+		int32_t k_prev2 = 0; float agree_prev2 = 1.0f; int64_t cut_prev2 = -1;
+		boundary_with_prev(V, k_prev2, agree_prev2, cut_prev2);
+		float min_final = agree_prev2;
+		for (float a : agree2) min_final = a < min_final ? a : min_final;
+		sh->agree_final[rank] = min_final;
+		int al = k_prev2 ? 0 : 1;
+		{
+			int s = k_prev2;
+			for (int32_t v : k2) { s += v; if (v) al = 0; }
+			sh->ksum2[rank] = s & 3;
+		}
+		sh->aligned[rank] = al;
+		/* where my last row ends: the cut against the next rank's first row, placed by MY row's symbols alone
+		 * (mid-way between two of them around the target), so both sides agree without talking */
+		int64_t hi_last = (int64_t)nsamples*L - 1;                  /* last rank: nothing from the zero padding */
+		if (!last && !rc && n >= 1) {
+			const size_t r = M - 1;
+			TRYCU(cudaMemcpy(d_two_q.p, d_q.as<char>() + r*q_stride, q_stride, cudaMemcpyDeviceToDevice));
+			TRYCU(cudaMemcpy(d_two_q.as<char>() + q_stride, d_q.as<char>() + r*q_stride, q_stride, cudaMemcpyDeviceToDevice));
+			const int32_t two_c[2] = { (int32_t)counts[r], (int32_t)counts[r] };
+			const int64_t two_b[2] = { base[r], base[r] };
+			TRYCU(cudaMemcpy(d_two_cnt.p, two_c, 8, cudaMemcpyHostToDevice));
+			TRYCU(cudaMemcpy(d_two_base.p, two_b, 16, cudaMemcpyHostToDevice));
+			DevBuf tgt, dcut, ia, ib, nav;
+			const int64_t t = cut_target(c1, V);
+			TRYCU(tgt.alloc(8)); TRYCU(dcut.alloc(8)); TRYCU(ia.alloc(4)); TRYCU(ib.alloc(4)); TRYCU(nav.alloc(4));
+			TRYCU(cudaMemcpy(tgt.p, &t, 8, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_find_cuts_device(d_two_q.as<uint32_t>(), q_stride, d_two_cnt.as<int32_t>(), d_two_base.as<int64_t>(), 2,
+			                                tgt.as<int64_t>(), dcut.as<int64_t>(), ia.as<int32_t>(), ib.as<int32_t>(), nav.as<int32_t>(), nullptr));
+			TRYCU(cudaMemcpy(&hi_last, dcut.p, 8, cudaMemcpyDeviceToHost));
+		}
+		sync();                                                     /* second round of quarter-turn sums */
+		std::vector<int32_t> turns(n > 0 ? n : 0, 0);
+		std::vector<int64_t> lo(n > 0 ? n : 0, -1), hi(n > 0 ? n : 0, LLONG_MAX);
+		if (n > 0) {
+			int kf = k_prev2;
+			for (int j = 0; j < rank; j++) kf += sh->ksum2[j];
+			turns[0] = kf & 3;
+			if (!first) lo[0] = cut_prev2;
+			for (int b = 0; b + 1 < n; b++) {
+				turns[b + 1] = (turns[b] + k2[b]) & 3;
+				hi[b] = cut2[b]; lo[b + 1] = cut2[b];
+			}
+			hi[n - 1] = hi_last;
+		}
+		DevBuf dlo, dhi, dst, dln, doff, dturn, dout;
+		std::vector<int32_t> len(n > 0 ? n : 0, 0), start(n > 0 ? n : 0, 0);
+		std::vector<int64_t> off(n > 0 ? n : 0, 0);
+		size_t total = 0, longest = 0;
+		if (n > 0) {
+			TRYCU(dlo.alloc(8*(size_t)n)); TRYCU(dhi.alloc(8*(size_t)n)); TRYCU(dst.alloc(4*(size_t)n)); TRYCU(dln.alloc(4*(size_t)n));
+			TRYCU(doff.alloc(8*(size_t)n)); TRYCU(dturn.alloc(4*(size_t)n));
+			TRYCU(cudaMemcpy(dlo.p, lo.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
+			TRYCU(cudaMemcpy(dhi.p, hi.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_ranges_device(q1, q_stride, cnt1, base1, n, dlo.as<int64_t>(), dhi.as<int64_t>(), dst.as<int32_t>(),
+			                             dln.as<int32_t>(), nullptr));
+			TRYCU(cudaMemcpy(len.data(), dln.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
+			TRYCU(cudaMemcpy(start.data(), dst.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
+			if (!rc) for (int b = 0; b < n; b++) { off[b] = (int64_t)total; total += (size_t)len[b]; longest = (size_t)len[b] > longest ? (size_t)len[b] : longest; }
+			TRYCU(dout.alloc(2*total));
+			TRYCU(cudaMemcpy(doff.p, off.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
+			TRYCU(cudaMemcpy(dturn.p, turns.data(), 4*(size_t)n, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_gather_device(soft1, soft_stride, n, longest, dst.as<int32_t>(), dln.as<int32_t>(), doff.as<int64_t>(),
+			                             dturn.as<int32_t>(), dout.as<int8_t>(), nullptr));
+		}
+		const size_t out_n = head.size()/2;                         /* rank 0: chunk 0's own symbols come first */
+		sh->nsym_rank[rank] = rc ? 0 : (long long)(out_n + total);
+
+		/* Stream-wide first lock (main.c:312 gates the output on pll_did_lock_once()). Chunk 0 may not have locked by the
+		 * end of its passes -- a recording that starts before the signal is up -- so the answer is the first OUTPUT symbol
+		 * that came from a loop which had locked once: row c's pass C inherits its predecessor's flag and symbol count
+		 * (exact for row 1, which continues chunk 0 bit for bit), so the row-local index at which it had locked is
+		 * first_lock_symbol - inherited count. Here: relative to this rank's own share. */
+		long long my_lock = -1;
+		if (!rc && n > 0 && h) {
+			const size_t tot_states = lrpt_states_size(h);
+			TRY(lrpt_export_states_device(h, d_states.p, tot_states, nullptr));
+			TRY(lrpt_sync(h, nullptr));
+			std::vector<lrpt_state_t> fin(M);
+			TRYCU(cudaMemcpy(fin.data(), d_states.p, M*sizeof(lrpt_state_t), cudaMemcpyDeviceToHost));
+			for (int b = 0; b < n && my_lock < 0 && !rc; b++) {
+				const lrpt_state_t &s = fin[(size_t)b + skip];
+				if (s.first_lock_symbol < 0 || len[b] <= 0) continue;
+				long long j = s.first_lock_symbol - nsym_start[(size_t)b + skip];   /* < 0: locked before this pass began */
+				if (j < start[b]) j = start[b];
+				if (j < (long long)start[b] + len[b]) my_lock = (long long)out_n + off[b] + (j - start[b]);
+			}
+		}
+		sh->first_lock_rank[rank] = my_lock;
+		sh->launches[rank] = h ? (int)lrpt_launch_count(h) : 0;
+		ph.mark("join (scan, ranges, gather)");
+		sync();                                                     /* every rank's symbol count is known: output offsets */
+		long long at = 0, all = 0;
+		for (int j = 0; j < world; j++) { if (j < rank) at += sh->nsym_rank[j]; all += sh->nsym_rank[j]; }
+		if (!rc && (size_t)all > job.cap) fail(LRPT_ERR_CAP);
+		if (!rc && !sh->failed()) {
+			if (!head.empty()) memcpy(job.soft + 2*(size_t)at, head.data(), head.size());
+			if (total) TRYCU(cudaMemcpy(job.soft + 2*((size_t)at + out_n), dout.p, 2*total, cudaMemcpyDeviceToHost));
+		}
+		ph.mark("D2H of the symbols");
+		if (st) cudaStreamDestroy(st);
+		sh->rc[rank] = rc;
+		return rc;
+#undef TRY
+#undef TRYCU
+	}
+};
+
+void *rank_main(void *arg) { static_cast<Rank *>(arg)->run(); return nullptr; }
+
 } // namespace
 
-extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shard_plan_t *plan, const void *raw_iq,
-                                    size_t nsamples, int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep)
+extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrpt_shard_plan_t *plan, const void *raw_iq,
+                                          size_t nsamples, int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep,
+                                          const int *devices, int ndev)
 {
-	if (!params || !plan || !raw_iq || !soft || !nsym) return LRPT_ERR_ARG;
+	if (!params || !plan || !raw_iq || !soft || !nsym || ndev < 1 || ndev > 64 || (ndev > 1 && !devices)) return LRPT_ERR_ARG;
 	const size_t C = plan->chunk, W = plan->warm, V = plan->overlap;
 	if (!C || !V || (C & 7) || (W & 7) || (V & 7) || params->oqpsk) return LRPT_ERR_ARG;   /* 16-byte aligned rows; QPSK ambiguity only */
 	if (params->bps != 8 && params->bps != 16 && params->bps != 32) return LRPT_ERR_ARG;
-	const size_t bytes = (size_t)params->bps/4;
-	const long long L = params->interp_factor;
 	const size_t M = nsamples > W ? (nsamples - W + C - 1)/C : 1;
 	if (M > (size_t)INT_MAX/2) return LRPT_ERR_ARG;
 	/* the rows' sub-step indices (sample*interp + sub-step, uint32 side output) must not wrap: the joins
@@ -116,188 +523,69 @@ extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shar
 	memset(&r, 0, sizeof(r));
 	r.nchunks = (int32_t)M; r.min_agreement_scan = r.min_agreement_final = 1.0f; r.first_lock_symbol = -1; r.aligned = 1;
 	*nsym = 0;
-	CK(cudaSetDevice(params->device));
-
-	Phases ph;
-	lrpt_params_t p = *params;
-	p.nstreams = (int32_t)M;
-	Handle hd;
-	RC(lrpt_create(&hd.h, &p));
-	lrpt_demod_t *h = hd.h;
+	const int dev0 = devices ? devices[0] : params->device;
 
 	if (M < 2) {                                                    /* one chunk: the sequential run itself, exact */
+		CK(cudaSetDevice(dev0));
+		lrpt_params_t p = *params;
+		p.nstreams = 1; p.device = dev0;
+		Handle hd;
+		RC(lrpt_create(&hd.h, &p));
 		size_t n = 0; long long fl = -1;
-		RC(lrpt_process(h, raw_iq, nsamples, soft, cap, &n, &fl));
-		*nsym = n; r.first_lock_symbol = fl; r.launches = (int32_t)lrpt_launch_count(h);
+		RC(lrpt_process(hd.h, raw_iq, nsamples, soft, cap, &n, &fl));
+		*nsym = n; r.first_lock_symbol = fl; r.launches = (int32_t)lrpt_launch_count(hd.h);
 		if (rep) *rep = r;
 		return LRPT_OK;
 	}
+	/* every rank needs a chunk, the one holding chunk 0 two (chunk 1 continues chunk 0 exactly) */
+	int world = ndev;
+	while (world > 1 && M/(size_t)world < 2) world--;
 
-	/* the stream on the device, zero padded so that every row can read W + C + 2V samples */
-	const size_t padded = (M - 1)*C + W + C + 2*V;
-	const size_t n_row = C + V;                                     /* samples of pass B / pass C */
-	const size_t cap_row = (symbol_capacity(W > n_row ? W : n_row, p) + 7)/8*8;
-	DevBuf d_raw, d_soft, d_q, d_nsym, d_cnt, d_base, d_states;
-	CK(d_raw.alloc(padded*bytes)); CK(d_soft.alloc(M*2*cap_row)); CK(d_q.alloc(M*4*cap_row)); CK(d_nsym.alloc(4*M));
-	CK(d_cnt.alloc(4*M)); CK(d_base.alloc(8*M));
-	ph.mark("handle + device buffers");
-	CK(cudaMemset(d_raw.as<char>() + nsamples*bytes, 0, (padded - nsamples)*bytes));
-	CK(cudaMemcpy(d_raw.p, raw_iq, nsamples*bytes, cudaMemcpyHostToDevice));
-	ph.mark("H2D of the recording");
-	RC(lrpt_set_symbol_index_output(h, d_q.as<uint32_t>(), 4*cap_row));
-	const char *raw0 = d_raw.as<char>();
-	const size_t soft_stride = 2*cap_row, q_stride = 4*cap_row;
-	std::vector<uint32_t> counts(M);
-	std::vector<int64_t> base(M);
-	auto run_pass = [&](size_t first_sample, size_t n) -> int {
-		RC(lrpt_process_batch_device(h, raw0 + first_sample*bytes, C*bytes, n, d_soft.as<int8_t>(), soft_stride, cap_row,
-		                             d_nsym.as<uint32_t>(), nullptr, 0, nullptr));
-		RC(lrpt_sync(h, nullptr));
-		RC(lrpt_get_counts(h, counts.data(), (int)M));
-		for (size_t c = 0; c < M; c++) if (counts[c] > cap_row) return LRPT_ERR_CAP;   /* the stitch kernels trust the counts */
-		for (size_t c = 0; c < M; c++) base[c] = (long long)(c*C + first_sample)*L;
-		CK(cudaMemcpy(d_cnt.p, counts.data(), 4*M, cudaMemcpyHostToDevice));   /* uint32 counts < 2^31: read as int32 */
-		CK(cudaMemcpy(d_base.p, base.data(), 8*M, cudaMemcpyHostToDevice));
-		return LRPT_OK;
-	};
-	auto cut_target = [&](size_t c, size_t shift) { return (long long)(W + c*C + shift + (V/4 < 64 ? V/4 : 64))*L; };
+	Shared sh;
+	sh.world = world;
+	sh.rc.assign(world, 0); sh.ksum.assign(world, 0); sh.ksum2.assign(world, 0); sh.aligned.assign(world, 1); sh.launches.assign(world, 0);
+	sh.agree_scan.assign(world, 1.0f); sh.agree_final.assign(world, 1.0f);
+	sh.nsym_rank.assign(world, 0); sh.first_lock_rank.assign(world, -1);
+	Nccl nccl;
+	if (world > 1) {
+		if (!nccl.load()) { fprintf(stderr, "lrpt_sharded_process_multi: libnccl.so.2 not found\n"); return LRPT_ERR_CUDA; }
+		sh.nccl = &nccl;
+		sh.comms.assign(world, nullptr);
+		if (nccl.CommInitAll(sh.comms.data(), world, devices)) return LRPT_ERR_CUDA;
+	}
+	pthread_barrier_init(&sh.bar, nullptr, (unsigned)world);
+	std::vector<Rank> ranks(world);
+	std::vector<pthread_t> tids(world);
+	for (int i = 0; i < world; i++) {
+		ranks[i].job = Job{ params, plan, static_cast<const uint8_t *>(raw_iq), nsamples, soft, cap, M };
+		ranks[i].sh = &sh; ranks[i].rank = i; ranks[i].dev = devices ? devices[i] : params->device;
+	}
+	for (int i = 1; i < world; i++) pthread_create(&tids[i], nullptr, rank_main, &ranks[i]);
+	ranks[0].run();
+	for (int i = 1; i < world; i++) pthread_join(tids[i], nullptr);
+	pthread_barrier_destroy(&sh.bar);
+	if (world > 1) for (int i = 0; i < world; i++) if (sh.comms[i]) nccl.CommDestroy(sh.comms[i]);
+	for (int i = 0; i < world; i++) if (sh.rc[i]) return sh.rc[i];
 
-	/* pass A: warm-up; chunk 0's warm-up symbols open the output (they are the sequential run's) */
-	size_t out_n = 0;
-	if (W) {
-		RC(run_pass(0, W));
-		if (counts[0] > cap) return LRPT_ERR_CAP;
-		CK(cudaMemcpy(soft, d_soft.p, 2*(size_t)counts[0], cudaMemcpyDeviceToHost));
-		out_n = counts[0];
+	long long total = 0, lock = sh.head_lock;
+	for (int i = 0; i < world; i++) {
+		if (lock < 0 && sh.first_lock_rank[i] >= 0) lock = total + sh.first_lock_rank[i];
+		total += sh.nsym_rank[i];
+		r.min_agreement_scan = sh.agree_scan[i] < r.min_agreement_scan ? sh.agree_scan[i] : r.min_agreement_scan;
+		r.min_agreement_final = sh.agree_final[i] < r.min_agreement_final ? sh.agree_final[i] : r.min_agreement_final;
+		if (!sh.aligned[i]) r.aligned = 0;
+		r.launches += sh.launches[i];
 	}
-	ph.mark("pass A (warm-up)");
-	/* pass B: owned + overlap, from the live state */
-	RC(run_pass(W, n_row));
-	ph.mark("pass B");
-	std::vector<int64_t> target(M - 1), cut;
-	std::vector<int32_t> k;
-	std::vector<float> agree;
-	for (size_t c = 1; c < M; c++) target[c - 1] = cut_target(c, 0);
-	RC(scan_rows(d_soft.as<int8_t>(), soft_stride, d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), (int)M,
-	             target, k, agree, cut));
-	for (float a : agree) r.min_agreement_scan = a < r.min_agreement_scan ? a : r.min_agreement_scan;
-	std::vector<int32_t> K(M, 0);
-	for (size_t c = 1; c < M; c++) K[c] = (K[c - 1] + k[c - 1]) & 3;
-	{
-		/* chunk 0's pass-B symbols continue the output, up to the end of the stream */
-		DevBuf lo, hi, st, ln;
-		const int64_t l = -1, hh = (int64_t)nsamples*L - 1;
-		int32_t s0 = 0, n0 = 0;
-		CK(lo.alloc(8)); CK(hi.alloc(8)); CK(st.alloc(4)); CK(ln.alloc(4));
-		CK(cudaMemcpy(lo.p, &l, 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(hi.p, &hh, 8, cudaMemcpyHostToDevice));
-		RC(lrpt_shard_ranges_device(d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), 1, lo.as<int64_t>(),
-		                            hi.as<int64_t>(), st.as<int32_t>(), ln.as<int32_t>(), nullptr));
-		CK(cudaMemcpy(&s0, st.p, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&n0, ln.p, 4, cudaMemcpyDeviceToHost));
-		if (out_n + (size_t)n0 > cap) return LRPT_ERR_CAP;
-		CK(cudaMemcpy(soft + 2*out_n, d_soft.as<int8_t>() + 2*(size_t)s0, 2*(size_t)n0, cudaMemcpyDeviceToHost));
-		out_n += (size_t)n0;
-		lrpt_status_t s;
-		RC(lrpt_status(h, 0, &s));
-		r.first_lock_symbol = s.first_lock_symbol;                  /* chunk 0 counts its symbols as the stream does */
-	}
-
-	ph.mark("quadrant scan + chunk 0");
-	const size_t out_head = out_n;                                  /* symbols of chunk 0's own trajectory (passes A + B) */
-	std::vector<long long> nsym_start(M, 0);                        /* symbol count row c inherits at the start of pass C */
-	/* hand-off: row c starts pass C from row c-1's end state, its Costas NCO turned back K[c-1] quarter turns
-	 * (p_phase = (float)((double)p_phase - K*pi/2), as lrpt_restore does; pll.c:16) */
-	{
-		const size_t total = lrpt_states_size(h), sb = sizeof(lrpt_state_t);
-		const size_t hb = (total - M*sb)/M;                         /* delay line bytes per row */
-		CK(d_states.alloc(total));
-		RC(lrpt_export_states_device(h, d_states.p, total, nullptr));
-		RC(lrpt_sync(h, nullptr));
-		std::vector<char> cur(total), nxt(total);
-		CK(cudaMemcpy(cur.data(), d_states.p, total, cudaMemcpyDeviceToHost));
-		lrpt_state_t *sc = reinterpret_cast<lrpt_state_t *>(cur.data()), *sn = reinterpret_cast<lrpt_state_t *>(nxt.data());
-		for (size_t c = 0; c < M; c++)
-			sc[c].p_phase = (float)((double)sc[c].p_phase - (double)(K[c] & 3)*1.57079632679489661923);
-		sn[0] = sc[0];                                              /* row 0 has no predecessor; its pass C is not used */
-		memcpy(nxt.data() + M*sb, cur.data() + M*sb, hb);
-		for (size_t c = 1; c < M; c++) {
-			sn[c] = sc[c - 1];
-			memcpy(nxt.data() + M*sb + c*hb, cur.data() + M*sb + (c - 1)*hb, hb);
-		}
-		for (size_t c = 0; c < M; c++) nsym_start[c] = sn[c].nsymbols;
-		CK(cudaMemcpy(d_states.p, nxt.data(), total, cudaMemcpyHostToDevice));
-		CK(cudaDeviceSynchronize());                                /* pageable upload on the legacy stream: not ordered with the handle's stream */
-		RC(lrpt_import_states_device(h, d_states.p, total, 1, nullptr));
-		RC(lrpt_sync(h, nullptr));
-	}
-
-	ph.mark("state hand-off");
-	/* pass C, then the join of rows 1 .. M-1 (rows 0 and 1 are one exact trajectory: nothing is cut off row 1's front) */
-	RC(run_pass(W + V, n_row));
-	ph.mark("pass C");
-	const int n = (int)M - 1;
-	const int8_t *soft1 = d_soft.as<int8_t>() + soft_stride;
-	const uint32_t *q1 = reinterpret_cast<const uint32_t *>(d_q.as<char>() + q_stride);
-	const int32_t *cnt1 = d_cnt.as<int32_t>() + 1;
-	const int64_t *base1 = d_base.as<int64_t>() + 1;
-	std::vector<int64_t> target2(n > 1 ? n - 1 : 0), cut2;
-	std::vector<int32_t> k2;
-	std::vector<float> agree2;
-	for (int b = 0; b + 1 < n; b++) target2[b] = cut_target((size_t)b + 2, V);
-	RC(scan_rows(soft1, soft_stride, q1, q_stride, cnt1, base1, n, target2, k2, agree2, cut2));
-	for (float a : agree2) r.min_agreement_final = a < r.min_agreement_final ? a : r.min_agreement_final;
-	std::vector<int32_t> turns(n, 0);
-	std::vector<int64_t> lo(n, -1), hi(n, LLONG_MAX);
-	for (int b = 0; b + 1 < n; b++) {
-		turns[b + 1] = (turns[b] + k2[b]) & 3;
-		if (k2[b]) r.aligned = 0;
-		hi[b] = cut2[b]; lo[b + 1] = cut2[b];
-	}
-	hi[n - 1] = (int64_t)nsamples*L - 1;                            /* nothing from the zero padding */
-	DevBuf dlo, dhi, dst, dln, doff, dturn, dout;
-	CK(dlo.alloc(8*(size_t)n)); CK(dhi.alloc(8*(size_t)n)); CK(dst.alloc(4*(size_t)n)); CK(dln.alloc(4*(size_t)n));
-	CK(doff.alloc(8*(size_t)n)); CK(dturn.alloc(4*(size_t)n));
-	CK(cudaMemcpy(dlo.p, lo.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(dhi.p, hi.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
-	RC(lrpt_shard_ranges_device(q1, q_stride, cnt1, base1, n, dlo.as<int64_t>(), dhi.as<int64_t>(), dst.as<int32_t>(),
-	                            dln.as<int32_t>(), nullptr));
-	std::vector<int32_t> len(n);
-	CK(cudaMemcpy(len.data(), dln.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
-	std::vector<int64_t> off(n);
-	size_t total = 0, longest = 0;
-	for (int b = 0; b < n; b++) { off[b] = (int64_t)total; total += (size_t)len[b]; longest = (size_t)len[b] > longest ? (size_t)len[b] : longest; }
-	if (out_n + total > cap) return LRPT_ERR_CAP;
-	CK(dout.alloc(2*total));
-	CK(cudaMemcpy(doff.p, off.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(dturn.p, turns.data(), 4*(size_t)n, cudaMemcpyHostToDevice));
-	RC(lrpt_shard_gather_device(soft1, soft_stride, n, longest, dst.as<int32_t>(), dln.as<int32_t>(), doff.as<int64_t>(),
-	                            dturn.as<int32_t>(), dout.as<int8_t>(), nullptr));
-	/* Stream-wide first lock (main.c:312 gates the output on pll_did_lock_once()). Chunk 0 may not have locked
-	 * by the end of its passes -- a recording that starts before the signal is up, the normal case for a
-	 * satellite pass -- so the answer is the first OUTPUT symbol that came from a loop which had locked once:
-	 * row c's pass C inherits its predecessor's flag and symbol count (exact for row 1, which continues chunk 0
-	 * bit for bit), so the row-local index at which it had locked is first_lock_symbol - inherited count. */
-	if (r.first_lock_symbol < 0) {
-		std::vector<int32_t> start(n);
-		CK(cudaMemcpy(start.data(), dst.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
-		const size_t tot_states = lrpt_states_size(h);
-		RC(lrpt_export_states_device(h, d_states.p, tot_states, nullptr));
-		RC(lrpt_sync(h, nullptr));
-		std::vector<lrpt_state_t> fin(M);
-		CK(cudaMemcpy(fin.data(), d_states.p, M*sizeof(lrpt_state_t), cudaMemcpyDeviceToHost));
-		for (int b = 0; b < n && r.first_lock_symbol < 0; b++) {
-			const lrpt_state_t &st = fin[(size_t)b + 1];
-			if (st.first_lock_symbol < 0 || len[b] <= 0) continue;
-			long long j = st.first_lock_symbol - nsym_start[(size_t)b + 1];     /* < 0: locked before this pass began */
-			if (j < start[b]) j = start[b];
-			if (j < (long long)start[b] + len[b]) r.first_lock_symbol = (long long)out_head + off[b] + (j - start[b]);
-		}
-	}
-	ph.mark("join (scan, ranges, gather)");
-	CK(cudaMemcpy(soft + 2*out_n, dout.p, 2*total, cudaMemcpyDeviceToHost));   /* default stream: ordered after the gather */
-	ph.mark("D2H of the symbols");
-	out_n += total;
-	*nsym = out_n;
-	r.launches = (int32_t)lrpt_launch_count(h);
+	r.first_lock_symbol = lock;
+	*nsym = (size_t)total;
+	r.launches /= world;                                            /* launches per GPU: the three passes */
 	if (rep) *rep = r;
 	return LRPT_OK;
+}
+
+extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shard_plan_t *plan, const void *raw_iq,
+                                    size_t nsamples, int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep)
+{
+	if (!params) return LRPT_ERR_ARG;
+	return lrpt_sharded_process_multi(params, plan, raw_iq, nsamples, soft, cap, nsym, rep, &params->device, 1);
 }

@@ -179,3 +179,26 @@ def test_port_equals_reference_on_random_parameters(oracle_mod):
         got = np.concatenate(parts)
         assert got.shape[0] == w.nsym and np.array_equal(got, w.soft), (trial, cfg)
         assert np.array_equal(bits(o.history()), bits(r.history())), (trial, cfg)
+
+
+def test_reference_power_on_image_restores_a_fresh_process(oracle_mod):
+    """bench.py's reference arm runs many power-on streams in ONE process: pyoracle.Ref(in_place=True).power_on() puts
+    the library's writable data back as it was right after loading (oracle/ref_driver.c). A stream demodulated after
+    power_on() must equal the same stream in a fresh private copy of the library, function-scope statics included
+    (OQPSK: timing.c:43, demod.c:54; the sweep direction: pll.c:112)."""
+    if not oracle_mod.have_ref("fma"):
+        pytest.skip("oracle/_ref not built")
+    from meteor_demod_b200 import synth
+    for cfg in (dict(symrate=72000, oqpsk=0, bps=16, order=32, interp=5), dict(symrate=80000, oqpsk=1, bps=8, order=32, interp=5)):
+        kw = dict(symrate=cfg["symrate"], oqpsk=bool(cfg["oqpsk"]), bps=cfg["bps"])
+        a = synth.make_raw(50_000, seed=5, cfo_hz=300.0, **kw)
+        b = synth.make_raw(40_000, seed=6, cfo_hz=-900.0, **kw)
+        for kind in ("strict", "fma"):
+            fresh = oracle_mod.Ref(kind=kind, **cfg).process(b)
+            r = oracle_mod.Ref(kind=kind, in_place=True, **cfg)
+            r.process(a)
+            r.power_on()
+            again = r.process(b)
+            assert again.nsym == fresh.nsym
+            assert np.array_equal(again.sym.view(np.uint32), fresh.sym.view(np.uint32)), (cfg, kind)
+            assert np.array_equal(again.lock_once, fresh.lock_once)

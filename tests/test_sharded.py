@@ -834,3 +834,35 @@ def test_gpu_engine_python_layer_on_cpu_stand_in(stream, monkeypatch):
     want = sharded.run_handoff(OracleEngine(raw, plan, cfg=OQ_CFG, seed_carrier=True), plan, oqpsk_half=OQ_HALF)
     got = _engine_run(monkeypatch, raw, OQ_CFG, plan, seed_carrier=True)
     assert np.array_equal(got["soft"].numpy(), want["soft"].numpy())
+
+
+@pytest.mark.gpu
+def test_c_level_multi_gpu_equals_one_gpu(stream, lib, tmp_path):
+    """lrpt_sharded_process_multi: the chunks of ONE recording over two GPUs driven from one process (a host thread per
+    device), boundary state and overlap symbols by ncclSend / ncclRecv -- byte-identical to the one-GPU call, report
+    included; and through the C host (--shard --gpus 2), whose output file equals the one-GPU run's."""
+    import subprocess
+    from meteor_demod_b200 import build, sharded, synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    kw = dict(chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16, rrc_order=32, interp_factor=5)
+    one, rep1 = sharded.process_host(stream, **kw)
+    two, rep2 = sharded.process_host(stream, devices=[0, 1], **kw)
+    assert one.shape == two.shape and np.array_equal(one, two)
+    assert rep2["nchunks"] == rep1["nchunks"] and rep2["first_lock_symbol"] == rep1["first_lock_symbol"]
+    assert rep2["aligned"] == rep1["aligned"] == 1 and rep2["launches"] == 3
+    assert abs(rep2["min_agreement_final"] - rep1["min_agreement_final"]) < 0.01
+    # devices in another order, and more devices than pairs of chunks (falls back to fewer ranks)
+    swapped, _ = sharded.process_host(stream, devices=[1, 0], **kw)
+    assert np.array_equal(swapped, one)
+    short = stream[: 2 * (WARM + 3 * CHUNK)]
+    a, _ = sharded.process_host(short, **kw)
+    b, _ = sharded.process_host(short, devices=[0, 1], **kw)
+    assert np.array_equal(a, b)
+    host = build.build_host()
+    wav = tmp_path / "in.wav"
+    wav.write_bytes(synth.wav_header(stream.nbytes) + stream.tobytes())
+    o1, o2 = tmp_path / "one.s", tmp_path / "two.s"
+    subprocess.run([host, "-B", "-q", "--shard", str(CHUNK), "-o", str(o1), str(wav)], check=True)
+    subprocess.run([host, "-B", "-q", "--shard", str(CHUNK), "--gpus", "2", "-o", str(o2), str(wav)], check=True)
+    assert o1.read_bytes() == o2.read_bytes() and o1.stat().st_size > 100_000
