@@ -103,7 +103,8 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 	/* shared memory carve-up */
 	uint64_t *full  = reinterpret_cast<uint64_t *>(smem_raw);       /* [S] */
 	uint64_t *empty = full + S;                                     /* [S] */
-	float *lut = reinterpret_cast<float *>(empty + S);              /* [32] */
+	uint64_t *chan  = empty + S;                                    /* [2] timing warp <-> loop warp hand-over signals */
+	float *lut = reinterpret_cast<float *>(chan + 2);               /* [32] */
 	MsgRD *r2d = reinterpret_cast<MsgRD *>(lut + 32);               /* [32] timing warp -> loop warp */
 	MsgDR *d2r = reinterpret_cast<MsgDR *>(r2d + 32);               /* [32] loop warp -> timing warp */
 	MsgDE *d2e = reinterpret_cast<MsgDE *>(d2r + 32);               /* [EG_RING][32] loop warp -> egress warp */
@@ -116,6 +117,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < S; s++) { mbar_init(&full[s], P); mbar_init(&empty[s], 1); }
+		mbar_init(&chan[0], 32); mbar_init(&chan[1], 32);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (threadIdx.x < 32) {
@@ -134,7 +136,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 #if LRPT_SPEC_SPLIT
 	if (warp >= 4 && (warp & 3) < 2) return;                        /* sub-partitions 0 and 1: timing warp, loop warp */
 	if (warp == 1) {
-		loop_warp_run<OQ>(c, a, lut, r2d, d2r, d2e, eack, lane, lane < Gc, g0);
+		loop_warp_run<OQ>(c, a, lut, r2d, d2r, chan, d2e, eack, lane, lane < Gc, g0);
 	} else if (warp == 2) {
 		egress_warp_run(a, d2e, eack, lane, lane < Gc, g0);
 	} else if (warp == 0) {
@@ -188,7 +190,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 				}
 				__syncwarp();
 				const int Qsym = Qx;
-				timing_round<OQ>(r, c, ready, y, round, r2d, d2r, lane, a.nco_n0, Q, q1, Qend, Qx, half, have_x);
+				timing_round<OQ>(r, c, ready, y, round, r2d, d2r, chan, lane, a.nco_n0, Q, q1, Qend, Qx, half, have_x);
 				if (ready) {
 					/* publish the timing state the FIR warps extrapolate from */
 					pubs[lane] = make_float4(__int_as_float(Qsym), r.t_phase, r.t_freq, nco_threshold(r, c));
@@ -205,6 +207,7 @@ demod_spec_kernel(const lrpt_consts_t c, const SpArgs a)
 		}
 		round++;
 		mbox_put4(&r2d[lane], 0.0f, 0.0f, MSG_STOP, round);
+		chan_signal(&chan[0]);
 		if (active) {                                               /* this warp's half of the state */
 			lrpt_state_t &s = a.states[sid];
 			s.t_phase = r.t_phase; s.t_freq = r.t_freq; s.t_prev = r.t_prev; s.t_dual_state = r.t_dual;
@@ -557,7 +560,7 @@ static int sp_nt(int taps, int T) { return 4 + (taps - 1 + T - 1)/T; }
 static size_t sp_fixed_smem(int taps, int L)
 {
 	const int LP = (L <= 4) ? 4 : 8;
-	return 2*SP_SLOTS*sizeof(uint64_t) + 32*sizeof(float) + 32*(sizeof(MsgRD) + sizeof(MsgDR) + sizeof(int)) + EG_RING*32*sizeof(MsgDE) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
+	return (2*SP_SLOTS + 2)*sizeof(uint64_t) + 32*sizeof(float) + 32*(sizeof(MsgRD) + sizeof(MsgDR) + sizeof(int)) + EG_RING*32*sizeof(MsgDE) + (size_t)((taps*LP + 3) & ~3)*sizeof(float);
 }
 
 static size_t sp_stream_smem(int taps, int T)
