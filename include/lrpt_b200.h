@@ -203,6 +203,12 @@ int  lrpt_shard_find_cuts_device(const uint32_t *d_q, size_t q_stride, const int
 int  lrpt_shard_quadrants_device(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride,
                                  const int64_t *d_base, int nrows, const int32_t *d_ia, const int32_t *d_ib, int npairs,
                                  int32_t *d_k, int32_t *d_same, void *cuda_stream);
+/* the same for OQPSK rows: the I arm is sampled half a symbol before the Q arm (demod.c:66-83), so an ODD quarter turn
+ * shows as a timing offset of half_substeps = fs*interp/(2*symrate) between paired symbols with the arms re-paired
+ * (meteor_demod_b200/sharded.py::boundary_quadrants_oqpsk); npairs must leave one symbol of row b in reserve */
+int  lrpt_shard_quadrants_oqpsk_device(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride,
+                                       const int64_t *d_base, int nrows, const int32_t *d_ia, const int32_t *d_ib, int npairs,
+                                       float half_substeps, int32_t *d_k, int32_t *d_same, void *cuda_stream);
 /* per row: the run of symbols with d_lo[r] < absolute sub-step <= d_hi[r] (INT64_MAX = to the end) */
 int  lrpt_shard_ranges_device(const uint32_t *d_q, size_t q_stride, const int32_t *d_count, const int64_t *d_base, int nrows,
                               const int64_t *d_lo, const int64_t *d_hi, int32_t *d_start, int32_t *d_len, void *cuda_stream);
@@ -218,7 +224,8 @@ int  lrpt_shard_gather_device(const int8_t *d_soft, size_t soft_stride, int nrow
  * chunks of `chunk` samples that run as the streams of a batch -- `warm` samples of warm-up before each
  * chunk, `overlap` samples into its successor (all multiples of 8; chunk + warm + overlap >= ~400 k samples
  * keeps the share of symbols off by more than one LSB at the 0.3-0.4 % of the reference's own FMA/strict
- * builds). The first two chunks are bit-exact. QPSK only; p->nstreams is ignored.
+ * builds). The first two chunks are bit-exact. QPSK and OQPSK (whose warm-up has to cover the
+ * reference's slow carrier pull-in: ~250 k samples at 700 Hz); p->nstreams is ignored.
  * soft: 2 int8 per symbol, ALL symbols in stream order (the host applies the 512-symbol lock gating with
  * rep->first_lock_symbol, which is chunk 0's: -1 if the loop had not locked by the end of chunk 0).
  */

@@ -81,7 +81,7 @@ struct Phases {
 /* boundaries between consecutive rows [r0, r0 + n): k, agreement and cut per boundary (host vectors) */
 int scan_rows(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride, const int32_t *d_count,
               const int64_t *d_base, int n, const std::vector<int64_t> &target, std::vector<int32_t> &k,
-              std::vector<float> &agree, std::vector<int64_t> &cut)
+              std::vector<float> &agree, std::vector<int64_t> &cut, float oqpsk_half = 0.0f)
 {
 	const int nb = n - 1;
 	k.assign(nb > 0 ? nb : 0, 0); agree.assign(nb > 0 ? nb : 0, 0.0f); cut.assign(nb > 0 ? nb : 0, 0);
@@ -97,9 +97,21 @@ int scan_rows(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, siz
 	CK(cudaMemcpy(cut.data(), dcut.p, 8*(size_t)nb, cudaMemcpyDeviceToHost));
 	int npairs = INT_MAX;
 	for (int v : navail) npairs = v < npairs ? v : npairs;
+	if (oqpsk_half > 0.0f) {
+		/* one symbol of the earlier row in reserve (the odd pairing reads a.I of the NEXT symbol), and every boundary
+		 * needs a symbol of that row in front of its first pair (sharded.py::boundary_quadrants_oqpsk) */
+		std::vector<int32_t> via(nb);
+		CK(cudaMemcpy(via.data(), ia.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
+		npairs = npairs > 0 ? npairs - 1 : 0;
+		for (int v : via) if (v <= 0) npairs = 0;
+	}
 	if (npairs < 8) return LRPT_OK;                                 /* k = 0, agreement = 0: the caller reports it */
-	RC(lrpt_shard_quadrants_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia.as<int32_t>(), ib.as<int32_t>(), npairs,
-	                               dk.as<int32_t>(), same.as<int32_t>(), nullptr));
+	if (oqpsk_half > 0.0f)
+		RC(lrpt_shard_quadrants_oqpsk_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia.as<int32_t>(), ib.as<int32_t>(), npairs,
+		                                     oqpsk_half, dk.as<int32_t>(), same.as<int32_t>(), nullptr));
+	else
+		RC(lrpt_shard_quadrants_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia.as<int32_t>(), ib.as<int32_t>(), npairs,
+		                               dk.as<int32_t>(), same.as<int32_t>(), nullptr));
 	std::vector<int32_t> s(nb);
 	CK(cudaMemcpy(k.data(), dk.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
 	CK(cudaMemcpy(s.data(), same.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
@@ -152,6 +164,29 @@ struct Job {
 	size_t M;                                                   /* chunks in the whole stream */
 };
 
+/* A row's loop state moved from the lock point it acquired to the one `turns` quarter turns back (the sequential run's).
+ * QPSK: the Costas NCO alone, p_phase = (float)((double)p_phase - turns*pi/2) (pll.c:16, as lrpt_restore does). OQPSK
+ * (sharded.py::turn_oqpsk_state): for an odd count the arms also change roles -- what was sampled as I at the pi crossing
+ * (timing.c:47-50) is the new Q and vice versa -- so the timing NCO moves by pi, the dual-threshold state toggles and the
+ * two remembered samples swap with the signs of the turn (demod.c:54, timing.c:13); half a turn flips both signs. */
+void turn_state(lrpt_state_t &s, int turns, bool oqpsk)
+{
+	const int kk = turns & 3;
+	s.p_phase = (float)((double)s.p_phase - (double)kk*1.57079632679489661923);
+	if (!oqpsk) return;
+	if (kk & 1) {
+		const double pi = 3.14159265358979323846, s_q = kk == 1 ? 1.0 : -1.0;
+		const float prev = s.t_prev, inph = s.oq_inphase;
+		s.t_phase = (float)((double)s.t_phase + (s.t_dual_state == 1 ? pi : -pi));
+		s.t_dual_state = 3 - s.t_dual_state;
+		s.t_prev = (float)(s_q*(double)inph);
+		s.oq_inphase = (float)(-s_q*(double)prev);
+	} else if (kk == 2) {
+		s.t_prev = -s.t_prev;
+		s.oq_inphase = -s.oq_inphase;
+	}
+}
+
 void split_rows(size_t M, int world, int rank, size_t &c0, size_t &c1)
 {
 	const size_t base = M/(size_t)world, extra = M%(size_t)world;
@@ -190,6 +225,8 @@ struct Rank {
 		split_rows(job.M, world, rank, c0, c1);
 		const size_t M = c1 - c0;
 		const bool first = rank == 0, last = rank == world - 1;
+		/* OQPSK: timing sub-steps in half a symbol; 0 = QPSK join */
+		const float oq_half = params.oqpsk ? (float)((double)params.samplerate*(double)params.interp_factor/(2.0*(double)params.symrate)) : 0.0f;
 		int rc = LRPT_OK;
 		Phases ph(first);
 		auto fail = [&](int code) { if (!rc) rc = code; sh->rc[rank] = rc; };
@@ -267,7 +304,7 @@ struct Rank {
 			std::vector<int32_t> k;
 			std::vector<float> ag;
 			TRY(scan_rows(d_two_soft.as<int8_t>(), soft_stride, d_two_q.as<uint32_t>(), q_stride, d_two_cnt.as<int32_t>(),
-			              d_two_base.as<int64_t>(), 2, tgt, k, ag, cut));
+			              d_two_base.as<int64_t>(), 2, tgt, k, ag, cut, oq_half));
 			if (!rc) { k_prev = k[0]; agree_prev = ag[0]; cut_prev = cut[0]; }
 		};
 
@@ -289,7 +326,7 @@ struct Rank {
 		std::vector<float> agree;
 		for (size_t c = 1; c < M; c++) target[c - 1] = cut_target(c0 + c, 0);
 		TRY(scan_rows(d_soft.as<int8_t>(), soft_stride, d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), (int)M,
-		              target, k, agree, cut));
+		              target, k, agree, cut, oq_half));
 		if (rc) { k.assign(M > 1 ? M - 1 : 0, 0); agree.assign(k.size(), 0.0f); }
 		int32_t k_prev = 0; float agree_prev = 1.0f; int64_t cut_prev = -1;
 		boundary_with_prev(0, k_prev, agree_prev, cut_prev);
@@ -347,8 +384,7 @@ struct Rank {
 			TRYCU(cudaMemcpy(cur.data(), d_states.p, total, cudaMemcpyDeviceToHost));
 			lrpt_state_t *sc = reinterpret_cast<lrpt_state_t *>(cur.data()), *sn = reinterpret_cast<lrpt_state_t *>(nxt.data());
 			if (!rc) {
-				for (size_t c = 0; c < M; c++)
-					sc[c].p_phase = (float)((double)sc[c].p_phase - (double)(K[c] & 3)*1.57079632679489661923);
+				for (size_t c = 0; c < M; c++) turn_state(sc[c], K[c], params.oqpsk != 0);
 				memcpy(io.data(), &sc[M - 1], sb);                  /* my last row's turned state -> the next rank */
 				memcpy(io.data() + sb, cur.data() + M*sb + (M - 1)*hb, hb);
 				TRYCU(cudaMemcpy(d_st_io.p, io.data(), one, cudaMemcpyHostToDevice));
@@ -392,7 +428,7 @@ struct Rank {
 		std::vector<int32_t> k2;
 		std::vector<float> agree2;
 		for (int b = 0; b + 1 < n; b++) target2[b] = cut_target(c0 + skip + (size_t)b + 1, V);
-		TRY(scan_rows(soft1, soft_stride, q1, q_stride, cnt1, base1, n, target2, k2, agree2, cut2));
+		TRY(scan_rows(soft1, soft_stride, q1, q_stride, cnt1, base1, n, target2, k2, agree2, cut2, oq_half));
 		if (rc) { k2.assign(n > 1 ? n - 1 : 0, 0); agree2.assign(k2.size(), 0.0f); cut2.assign(k2.size(), 0); }
 		int32_t k_prev2 = 0; float agree_prev2 = 1.0f; int64_t cut_prev2 = -1;
 		boundary_with_prev(V, k_prev2, agree_prev2, cut_prev2);
@@ -512,7 +548,7 @@ extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrp
 {
 	if (!params || !plan || !raw_iq || !soft || !nsym || ndev < 1 || ndev > 64 || (ndev > 1 && !devices)) return LRPT_ERR_ARG;
 	const size_t C = plan->chunk, W = plan->warm, V = plan->overlap;
-	if (!C || !V || (C & 7) || (W & 7) || (V & 7) || params->oqpsk) return LRPT_ERR_ARG;   /* 16-byte aligned rows; QPSK ambiguity only */
+	if (!C || !V || (C & 7) || (W & 7) || (V & 7)) return LRPT_ERR_ARG;             /* 16-byte aligned rows for every sample format */
 	if (params->bps != 8 && params->bps != 16 && params->bps != 32) return LRPT_ERR_ARG;
 	const size_t M = nsamples > W ? (nsamples - W + C - 1)/C : 1;
 	if (M > (size_t)INT_MAX/2) return LRPT_ERR_ARG;

@@ -113,6 +113,89 @@ __global__ void shard_quadrants_kernel(const int8_t *soft, size_t soft_stride, c
 	}
 }
 
+/* OQPSK boundaries (meteor_demod_b200/sharded.py::boundary_quadrants_oqpsk, same arithmetic in integers): the I arm is
+ * sampled half a symbol before the Q arm (demod.c:66-83) and the timing detector reads only Q (timing.c:65), so at an
+ * ODD number of quarter turns the later row takes its symbols `half` sub-steps off, its Q arm carrying the earlier
+ * row's I stream and its I arm the earlier row's Q stream of the symbol before: b.Q_j = -+a.I_{m+1}, b.I_j = +-a.Q_m
+ * with q_b[j] ~ q_a[m] + half. The median timing offset of the paired symbols tells even from odd, a correlation
+ * picks the sign. One block per boundary; npairs <= what find_cuts reported minus one symbol of row a in reserve. */
+__global__ void shard_quadrants_oqpsk_kernel(const int8_t *soft, size_t soft_stride, const uint32_t *q, size_t q_stride,
+                                             const long long *base, const int32_t *ia_in, const int32_t *ib_in, int npairs,
+                                             float half_substeps, int32_t *k_out, int32_t *same_out)
+{
+	const int b = blockIdx.x;
+	const int ia = ia_in[b], ib = ib_in[b];
+	const char2 *ra = reinterpret_cast<const char2 *>(soft + (size_t)b*soft_stride);
+	const char2 *sb = reinterpret_cast<const char2 *>(soft + (size_t)(b + 1)*soft_stride) + ib;
+	const uint32_t *qa = qrow(q, q_stride, b) + ia, *qb = qrow(q, q_stride, b + 1) + ib;
+	const long long dbase = base[b + 1] - base[b];                  /* d = q_b - q_a in absolute sub-steps */
+	__shared__ int hist[257];
+	__shared__ long long red0[32], red1[32];
+	__shared__ int s_dm, s_k, reds[32];
+	for (int i = threadIdx.x; i < 257; i += blockDim.x) hist[i] = 0;
+	__syncthreads();
+	for (int j = threadIdx.x; j < npairs; j += blockDim.x) {
+		long long d = (long long)qb[j] - (long long)qa[j] + dbase;
+		d = d < -128 ? -128 : d > 128 ? 128 : d;
+		atomicAdd(&hist[(int)d + 128], 1);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {                                         /* lower median, as torch.median */
+		const int want = (npairs - 1)/2 + 1;
+		int cum = 0, v = 0;
+		for (v = 0; v < 257; v++) { cum += hist[v]; if (cum >= want) break; }
+		s_dm = v - 128;
+	}
+	__syncthreads();
+	const int dm = s_dm;
+	const bool odd = fabsf((float)dm) > half_substeps*0.5f;
+	const int off = dm > 0 ? 0 : -1;
+	long long s0 = 0, s1 = 0;                                       /* even score, odd score */
+	for (int j = threadIdx.x; j < npairs; j += blockDim.x) {
+		const char2 a = ra[ia + j], c = sb[j];
+		int m = ia + j + off;
+		m = m < 0 ? 0 : m;
+		const int aQm = ra[m].y, aIm1 = ra[m + 1].x;
+		s0 += (int)a.x*c.x + (int)a.y*c.y;
+		s1 += -aIm1*(int)c.y + aQm*(int)c.x;
+	}
+	for (int o = 16; o; o >>= 1) { s0 += __shfl_down_sync(0xffffffffu, s0, o); s1 += __shfl_down_sync(0xffffffffu, s1, o); }
+	if ((threadIdx.x & 31) == 0) { red0[threadIdx.x >> 5] = s0; red1[threadIdx.x >> 5] = s1; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		long long t0 = 0, t1 = 0;
+		for (int w = 0; w < (int)(blockDim.x + 31)/32; w++) { t0 += red0[w]; t1 += red1[w]; }
+		s_k = odd ? (t1 >= 0 ? 1 : 3) : (t0 >= 0 ? 0 : 2);
+	}
+	__syncthreads();
+	const int k = s_k;
+	const int sg = (k == 0 || k == 1) ? 1 : -1;
+	int same = 0;
+	for (int j = threadIdx.x; j < npairs; j += blockDim.x) {
+		const char2 a = ra[ia + j], c = sb[j];
+		long long d = (long long)qb[j] - (long long)qa[j] + dbase;
+		if (!odd) {
+			const long long ad = d < 0 ? -d : d;
+			same += (sign3(sg*c.x) == sign3(a.x)) && (sign3(sg*c.y) == sign3(a.y)) && ad <= 2;
+		} else {
+			int m = ia + j + off;
+			m = m < 0 ? 0 : m;
+			const int aQm = ra[m].y, aIm1 = ra[m + 1].x;
+			long long dd = d - dm;
+			dd = dd < 0 ? -dd : dd;
+			same += (sign3(-sg*c.y) == sign3(aIm1)) && (sign3(sg*c.x) == sign3(aQm)) && dd <= 2;
+		}
+	}
+	for (int o = 16; o; o >>= 1) same += __shfl_down_sync(0xffffffffu, same, o);
+	if ((threadIdx.x & 31) == 0) reds[threadIdx.x >> 5] = same;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int t = 0;
+		for (int w = 0; w < (int)(blockDim.x + 31)/32; w++) t += reds[w];
+		k_out[b] = k; same_out[b] = t;
+	}
+}
+
 /* symbols of row r with lo < q <= hi: a contiguous run, because q ascends */
 __global__ void shard_ranges_kernel(const uint32_t *q, size_t q_stride, const int32_t *count, const long long *base, int M,
                                     const long long *lo, const long long *hi, int32_t *start, int32_t *len)
@@ -173,6 +256,18 @@ extern "C" int lrpt_shard_quadrants_device(const int8_t *d_soft, size_t soft_str
 	if (nrows < 2) return LRPT_OK;
 	shard_quadrants_kernel<<<nrows - 1, 256, 0, (cudaStream_t)cuda_stream>>>(
 		d_soft, soft_stride, d_q, q_stride, reinterpret_cast<const long long *>(d_base), d_ia, d_ib, npairs, d_k, d_same);
+	return done(cudaGetLastError());
+}
+
+extern "C" int lrpt_shard_quadrants_oqpsk_device(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride,
+                                                 const int64_t *d_base, int nrows, const int32_t *d_ia, const int32_t *d_ib, int npairs,
+                                                 float half_substeps, int32_t *d_k, int32_t *d_same, void *cuda_stream)
+{
+	if (!d_soft || !d_q || !d_base || !d_ia || !d_ib || !d_k || !d_same || nrows < 1 || npairs < 0 || (q_stride & 3) || (soft_stride & 1))
+		return LRPT_ERR_ARG;
+	if (nrows < 2) return LRPT_OK;
+	shard_quadrants_oqpsk_kernel<<<nrows - 1, 256, 0, (cudaStream_t)cuda_stream>>>(
+		d_soft, soft_stride, d_q, q_stride, reinterpret_cast<const long long *>(d_base), d_ia, d_ib, npairs, half_substeps, d_k, d_same);
 	return done(cudaGetLastError());
 }
 

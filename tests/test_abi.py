@@ -92,7 +92,7 @@ def test_sharded_entry_point_checks_arguments_and_needs_a_gpu(lib):
     import torch
     from meteor_demod_b200 import LrptError, sharded
     raw = np.zeros(2 * 4096, np.int16)
-    for bad in (dict(chunk=1001), dict(warm=12), dict(overlap=0), dict(oqpsk=True), dict(bps=12)):
+    for bad in (dict(chunk=1001), dict(warm=12), dict(overlap=0), dict(bps=12)):
         kw = dict(chunk=1024, warm=512, overlap=64, symrate=72000, bps=16)
         kw.update(bad)
         with pytest.raises(LrptError) as e:

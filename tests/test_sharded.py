@@ -487,6 +487,31 @@ def test_gpu_oqpsk_handoff_equals_oracle_handoff(lib, oracle_mod):
 
 
 @pytest.mark.gpu
+def test_c_entry_point_oqpsk_equals_python_handoff(lib, oracle_mod):
+    """lrpt_sharded_process for OQPSK (csrc/shard_stitch.cu::shard_quadrants_oqpsk_kernel, shard_run.cu::turn_state) against
+    the torch-orchestrated hand-off run on the GPU engine: same kernels for the passes, the same join arithmetic in
+    integers, so byte-identical; odd quarter turns occur in this stream."""
+    from meteor_demod_b200 import sharded
+    raw = make_oqpsk_stream()
+    n = raw.size // 2
+    plan = sharded.Plan(n, CHUNK, WARM, OVERLAP, OQ_CFG["interp"])
+    dev = torch.zeros(2 * plan.padded, dtype=torch.uint8, device="cuda")
+    dev[: raw.size] = torch.from_numpy(raw).cuda()
+    kw = dict(chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=80000, oqpsk=True, bps=8, rrc_order=32, interp_factor=5)
+    want = sharded.demod_sharded(dev, n, handoff=True, **kw)
+    assert any(int(k) % 2 for k in want["first_pass"]["K"])
+    got, rep = sharded.process_host(raw, **kw)
+    assert np.array_equal(got, want["soft"].cpu().numpy())
+    assert rep["aligned"] == 1 and rep["nchunks"] == plan.nchunks
+    assert abs(rep["min_agreement_final"] - float(want["agreement"].min())) < 1e-6
+    seq = oracle_mod.Oracle(**OQ_CFG).process(raw, want_float=False)
+    assert got.shape[0] == seq.nsym
+    if torch.cuda.device_count() >= 2:
+        two, _ = sharded.process_host(raw, devices=[0, 1], **kw)
+        assert np.array_equal(two, got)
+
+
+@pytest.mark.gpu
 def test_gpu_seeded_warm_up(lib, oracle_mod):
     """seed_carrier on the GPU engine: OQPSK at +1200 Hz, where cold chunks cannot lock within the warm-up. The coarse
     estimate is an FFT in float32 (on the GPU here, on the CPU in the oracle-driven test), so the seed may differ in
@@ -557,8 +582,6 @@ def test_single_call_c_entry_point_equals_python_handoff(stream, lib):
     assert rep2["nchunks"] == 2 and np.array_equal(got2, w2.soft)          # chunks 0 and 1 are exact
     with pytest.raises(LrptError):
         sharded.process_host(stream, chunk=CHUNK + 4, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
-    with pytest.raises(LrptError):
-        sharded.process_host(stream, chunk=CHUNK, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16, oqpsk=True)
 
 
 def random_rows(g, M, C, V, L):
