@@ -633,7 +633,8 @@ def bench_frontend(local, rank, nframes_block=64, tiles=128):
             fe.viterbi_cadu(block, f * fe.CADU_SYMS, 1)
         t2 = time.perf_counter()
         rec["cpu_oracle_1core"] = {"sync_msym_s": n_cpu / (t1 - t0) / 1e6, "viterbi_msym_s": 8 * fe.CADU_SYMS / (t2 - t1) / 1e6}
-        same = bool(np.array_equal(score[:n_cpu].cpu().numpy(), s_c) and np.array_equal(hyp[:n_cpu].cpu().numpy(), h_c))
+        m = n_cpu - 31                                       # the last 31 windows of the head run past its end
+        same = bool(np.array_equal(score[:m].cpu().numpy(), s_c[:m]) and np.array_equal(hyp[:m].cpu().numpy(), h_c[:m]))
         c0, _ = fe.viterbi_cadu(head, 3 * fe.CADU_SYMS, 1)
         rec["equals_oracle"] = bool(same and np.array_equal(cadu[3].cpu().numpy(), c0))
     return rec

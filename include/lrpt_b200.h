@@ -154,6 +154,17 @@ int  lrpt_process_batch_device(lrpt_demod_t *h, const void *d_raw_iq, size_t raw
  */
 int  lrpt_set_symbol_index_output(lrpt_demod_t *h, uint32_t *d_index, size_t stride);
 int  lrpt_sync(lrpt_demod_t *h, void *cuda_stream);
+/*
+ * Ordering against the caller's streams without blocking the host. The handle's own stream (the one a NULL
+ * cuda_stream argument selects) is non-blocking: it is NOT ordered with the legacy default stream or any other.
+ *   lrpt_stream_wait:    everything enqueued on producer_stream so far (NULL = the legacy default stream)
+ *                        completes before anything enqueued on the handle's stream from now on starts -- call it
+ *                        after filling the raw buffer / clearing the soft buffer on your stream;
+ *   lrpt_stream_release: the reverse, for a consumer_stream that reads the symbols.
+ * (The reference is synchronous, demod.c:25-58; these have no counterpart there.)
+ */
+int  lrpt_stream_wait(lrpt_demod_t *h, void *producer_stream);
+int  lrpt_stream_release(lrpt_demod_t *h, void *consumer_stream);
 /* per-stream symbol counts of the most recent call (host copy; call after lrpt_sync) */
 int  lrpt_get_counts(lrpt_demod_t *h, uint32_t *nsym, int nstreams);
 
@@ -301,6 +312,8 @@ int   lrpt_unpin_host(void *p);
  * 8*L bytes out and 4*taps*L flops per sample) and compared value by value with filter_get.
  * mode 0: multiply and add rounded separately, oldest tap first -- bit-identical to filter_get;
  * mode 1: fused multiply-add (one rounding per tap; statistical parity only).
+ * Bits 1-2 of mode are a tuning knob: output samples per thread (0 = chosen by filter length, 1 or 2);
+ * the results do not depend on it.
  * Strides in bytes, pointers and strides 16-byte aligned, interp_factor <= 8, taps <= 257; asynchronous on
  * `cuda_stream` except for a short synchronisation while the tap table is uploaded. */
 int  lrpt_fir_stage_device(const lrpt_params_t *p, const void *d_raw, size_t raw_stride, int nrows, size_t nsamples,

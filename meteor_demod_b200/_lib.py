@@ -62,6 +62,8 @@ SYMBOLS = {
                                             C.c_void_p]),
     "lrpt_set_symbol_index_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "lrpt_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lrpt_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lrpt_stream_release": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lrpt_get_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lrpt_status": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Status)]),
     "lrpt_state_size": (C.c_size_t, [C.c_void_p]),

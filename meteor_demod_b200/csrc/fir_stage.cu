@@ -15,8 +15,9 @@
  * TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one thread, the next
  * tile's copy in flight while this tile is filtered; raw samples are converted once per tile to a float2
  * window (wavfile.c:58-69); thread = output sample, L packed-f32x2 accumulators (I and Q of one phase ride
- * one FMUL2 + FFMA2 pair), the window read conflict-free (consecutive threads, consecutive samples), the taps
- * as broadcasts; outputs go out as 8-byte stores, L consecutive per thread.
+ * one FMUL2 + FFMA2 pair) for each of TWO samples half a tile apart, so every coefficient load feeds 2*L
+ * multiply-accumulates (one sample per thread for short filters); the window is read conflict-free (consecutive threads, consecutive samples), the taps as
+ * broadcasts; outputs go out as 8-byte stores, L consecutive per thread.
  *
  * mode 0 ("exact"): acc = RN(acc + RN(x*h)), oldest tap first -- bit-identical to filter_get at every
  * (n, i); two instructions per tap and phase. mode 1 ("fma"): acc = RN(acc + x*h), one instruction per tap
@@ -89,8 +90,8 @@ template <> LRPT_DEV float2 fs_cvt<8>(const uint8_t *raw, int i)
 }
 template <> LRPT_DEV float2 fs_cvt<32>(const uint8_t *raw, int i) { return reinterpret_cast<const float2 *>(raw)[i]; }
 
-template <int L, int BPS, bool FMA>
-__global__ void __launch_bounds__(FS_THREADS, 2)
+template <int L, int BPS, bool FMA, int NS>
+__global__ void __launch_bounds__(FS_THREADS, 3)
 fir_stage_kernel(const FirStageArgs a)
 {
 	constexpr int LP = (L <= 4) ? 4 : 8;
@@ -159,47 +160,64 @@ fir_stage_kernel(const FirStageArgs a)
 
 		float2 *orow = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.out) + (size_t)row*a.out_stride);
 		const int off = HP - (taps - 1);                                /* window entry of the oldest tap of local sample 0 */
+		/* NS = 2: two output samples per thread (tile halves), so that every coefficient load feeds 2*L
+		 * multiply-accumulates (long filters: the FMA pipe is the bound); NS = 1: one sample per thread (short
+		 * filters: more independent threads per tile to cover the stores) */
 #pragma unroll 1
-		for (int nl = tid; nl < T; nl += FS_THREADS) {
-			const int n = t*T + nl;
-			if (n >= a.nsamples) break;
-			const float2 *w = xf + off + nl;
-			fs2_t acc[L];
+		for (int nl = tid; nl < T/NS; nl += FS_THREADS) {
+			const int n0 = t*T + nl, n1 = n0 + T/2;
+			if (n0 >= a.nsamples) break;
+			const float2 *w0 = xf + off + nl, *w1 = w0 + T/2;
+			fs2_t acc0[L], acc1[NS == 2 ? L : 1];
 #pragma unroll
-			for (int p = 0; p < L; p++) acc[p] = fs_pk(0.0f, 0.0f);
+			for (int p = 0; p < L; p++) { acc0[p] = fs_pk(0.0f, 0.0f); if (NS == 2) acc1[p] = fs_pk(0.0f, 0.0f); }
 #pragma unroll 4
 			for (int k = 0; k < taps; k++) {
-				const float2 x = w[k];
-				const fs2_t x2 = fs_pk(x.x, x.y);
+				const float2 xa = w0[k];
+				const fs2_t xa2 = fs_pk(xa.x, xa.y);
+				fs2_t xb2 = xa2;
+				if (NS == 2) { const float2 xb = w1[k]; xb2 = fs_pk(xb.x, xb.y); }
 				float hv[LP];
 				*reinterpret_cast<float4 *>(hv) = *reinterpret_cast<const float4 *>(hT + k*LP);
 				if (LP == 8) *reinterpret_cast<float4 *>(hv + 4) = *reinterpret_cast<const float4 *>(hT + k*LP + 4);
 #pragma unroll
 				for (int p = 0; p < L; p++) {
 					const fs2_t h2 = fs_pk(hv[p], hv[p]);
-					if (FMA) acc[p] = fs_fma(x2, h2, acc[p]);
-					else     acc[p] = fs_fma(fs_mul(x2, h2), one2, acc[p]);   /* RN(acc + RN(x*h)): filter.c:57-62 */
+					if (FMA) {
+						acc0[p] = fs_fma(xa2, h2, acc0[p]);
+						if (NS == 2) acc1[p] = fs_fma(xb2, h2, acc1[p]);
+					} else {                                        /* RN(acc + RN(x*h)): filter.c:57-62 */
+						acc0[p] = fs_fma(fs_mul(xa2, h2), one2, acc0[p]);
+						if (NS == 2) acc1[p] = fs_fma(fs_mul(xb2, h2), one2, acc1[p]);
+					}
 				}
 			}
 			/* sub-step i reads bank L-1-i (filter.c:52) */
 #pragma unroll
-			for (int i = 0; i < L; i++) orow[(size_t)n*L + i] = fs_upk(acc[L - 1 - i]);
+			for (int i = 0; i < L; i++) orow[(size_t)n0*L + i] = fs_upk(acc0[L - 1 - i]);
+			if (NS == 2 && n1 < a.nsamples) {
+#pragma unroll
+				for (int i = 0; i < L; i++) orow[(size_t)n1*L + i] = fs_upk(acc1[L - 1 - i]);
+			}
 		}
 		__syncthreads();                                               /* xf is rewritten by the next item */
 	}
 }
 
-template <int L, int BPS> static cudaError_t fs_launch2(const FirStageArgs &a, int mode, int blocks, size_t smem, cudaStream_t st)
+template <int L, int BPS, bool FMA, int NS> static cudaError_t fs_launch3(const FirStageArgs &a, int blocks, size_t smem, cudaStream_t st)
 {
 	cudaError_t e;
-	if (mode) {
-		if ((e = cudaFuncSetAttribute(fir_stage_kernel<L, BPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-		fir_stage_kernel<L, BPS, true><<<blocks, FS_THREADS, smem, st>>>(a);
-	} else {
-		if ((e = cudaFuncSetAttribute(fir_stage_kernel<L, BPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-		fir_stage_kernel<L, BPS, false><<<blocks, FS_THREADS, smem, st>>>(a);
-	}
+	if ((e = cudaFuncSetAttribute(fir_stage_kernel<L, BPS, FMA, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+	fir_stage_kernel<L, BPS, FMA, NS><<<blocks, FS_THREADS, smem, st>>>(a);
 	return cudaGetLastError();
+}
+
+template <int L, int BPS> static cudaError_t fs_launch2(const FirStageArgs &a, int mode, int blocks, size_t smem, cudaStream_t st)
+{
+	int ns = (mode >> 1) & 3;                                           /* 0 = by filter length */
+	if (ns == 0) ns = a.taps*L >= 160 ? 2 : 1;
+	if (mode & 1) return ns == 2 ? fs_launch3<L, BPS, true, 2>(a, blocks, smem, st) : fs_launch3<L, BPS, true, 1>(a, blocks, smem, st);
+	return ns == 2 ? fs_launch3<L, BPS, false, 2>(a, blocks, smem, st) : fs_launch3<L, BPS, false, 1>(a, blocks, smem, st);
 }
 
 template <int L> static cudaError_t fs_launch1(const FirStageArgs &a, int bps, int mode, int blocks, size_t smem, cudaStream_t st)
@@ -245,7 +263,7 @@ extern "C" int lrpt_fir_stage_device(const lrpt_params_t *p, const void *d_raw, 
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
 	const int tiles = (int)((nsamples + FS_TILE - 1)/FS_TILE);
 	const long long items = (long long)nrows*tiles;
-	const int blocks = (int)(items < 2LL*sms ? items : 2LL*sms);      /* persistent: two CTAs per SM */
+	const int blocks = (int)(items < 3LL*sms ? items : 3LL*sms);      /* persistent: three CTAs per SM */
 	const size_t smem = 128 + (size_t)((taps*LP*4 + 127)/128)*128 + (size_t)(((a.HP + FS_TILE)*bytes + 127)/128)*128 +
 	                    (size_t)(a.HP + FS_TILE)*8;
 	cudaError_t e;

@@ -39,6 +39,7 @@ struct lrpt_demod {
 	lrpt_state_t *h_state  = nullptr;   /* pinned scratch, one state */
 	cudaStream_t  stream = nullptr, copy_stream = nullptr, out_stream = nullptr;
 	cudaEvent_t   ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_cnt[2] = {nullptr, nullptr};
+	cudaEvent_t   ev_order = nullptr;   /* lrpt_stream_wait / lrpt_stream_release */
 	uint32_t     *d_mm = nullptr;       /* [2][2] min/max append cursor after a slab */
 	uint32_t     *h_mm = nullptr;       /* pinned copy */
 	/* staging for the host-buffer entry points (grown on demand) */
@@ -208,6 +209,7 @@ extern "C" void lrpt_destroy(lrpt_demod_t *h)
 		if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
 		if (h->ev_cnt[i]) cudaEventDestroy(h->ev_cnt[i]);
 	}
+	if (h->ev_order) cudaEventDestroy(h->ev_order);
 	if (h->out_stream) cudaStreamDestroy(h->out_stream);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -300,6 +302,29 @@ extern "C" int lrpt_sync(lrpt_demod_t *h, void *cuda_stream)
 	CU(h, cudaSetDevice(h->p.device));
 	CU(h, cudaStreamSynchronize(cuda_stream ? (cudaStream_t)cuda_stream : h->stream));
 	return LRPT_OK;
+}
+
+/* Stream ordering without a host synchronisation: the handle's own stream is created non-blocking, so work a
+ * caller enqueued on ANOTHER stream (the legacy default stream included: pass NULL) is not ordered with it. */
+static int order_streams(lrpt_demod *h, cudaStream_t first, cudaStream_t then)
+{
+	CU(h, cudaSetDevice(h->p.device));
+	if (!h->ev_order) CU(h, cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+	CU(h, cudaEventRecord(h->ev_order, first));
+	CU(h, cudaStreamWaitEvent(then, h->ev_order, 0));
+	return LRPT_OK;
+}
+
+extern "C" int lrpt_stream_wait(lrpt_demod_t *h, void *producer_stream)
+{
+	if (!h) return LRPT_ERR_ARG;
+	return order_streams(h, (cudaStream_t)producer_stream, h->stream);
+}
+
+extern "C" int lrpt_stream_release(lrpt_demod_t *h, void *consumer_stream)
+{
+	if (!h) return LRPT_ERR_ARG;
+	return order_streams(h, h->stream, (cudaStream_t)consumer_stream);
 }
 
 extern "C" int lrpt_get_counts(lrpt_demod_t *h, uint32_t *nsym, int nstreams)

@@ -139,11 +139,20 @@ class Demod:
         self.last_rc = rc
         return (soft, counts, symf) if want_float else (soft, counts)
 
+    def _after_torch(self, tensor, stream):
+        """The handle's own stream is non-blocking: order it after whatever torch has enqueued on ITS current
+        stream for `tensor`'s device (the copy / fill that produced the buffers), without a host sync."""
+        if stream is None and getattr(tensor, "is_cuda", False):
+            import torch
+            cur = torch.cuda.current_stream(tensor.device).cuda_stream
+            self._check(self.lib.lrpt_stream_wait(self.h, C.c_void_p(cur) if cur else None), "stream_wait")
+
     def process_device(self, raw, soft, nsym=None, symf=None, stream=None, nsamples=None):
         """All streams, device buffers (torch tensors). Asynchronous on `stream` (torch.cuda.Stream
-        or None = the handle's own stream). raw: [nstreams, 2*nsamples] of the raw dtype;
-        soft: int8 [nstreams, 2*cap]; nsym: optional uint32/int32 [nstreams]; symf: optional float32
-        [nstreams, 2*cap]."""
+        or None = the handle's own stream, ordered after torch's current stream). raw: [nstreams, 2*nsamples] of
+        the raw dtype; soft: int8 [nstreams, 2*cap]; nsym: optional uint32/int32 [nstreams]; symf: optional float32
+        [nstreams, 2*cap]. Reading the results with torch ops needs sync() (or the same `stream`) first."""
+        self._after_torch(raw, stream)
         if raw.dim() != 2 or raw.shape[0] != self.nstreams or soft.shape[0] != self.nstreams:
             raise ValueError("raw/soft must be [nstreams, ...]")
         n = raw.shape[1] // 2 if nsamples is None else int(nsamples)
@@ -234,6 +243,7 @@ class Demod:
                     "export_states_device")
 
     def import_states_device(self, buf, check=True, stream=None):
+        self._after_torch(buf, stream)
         st = C.c_void_p(stream.cuda_stream) if stream is not None else None
         self._check(self.lib.lrpt_import_states_device(self.h, buf.data_ptr(), buf.numel() * buf.element_size(),
                                                        int(check), st), "import_states_device")

@@ -527,9 +527,7 @@ class GpuEngine:
         import ctypes as C
         sb = C.sizeof(State)
         buf = torch.cat((rows[:, :sb].reshape(-1), rows[:, sb:].reshape(-1))).contiguous()
-        if buf.is_cuda:
-            torch.cuda.current_stream(buf.device).synchronize()  # the rows were produced on torch's stream (recv, cat);
-        self.d.import_states_device(buf, check=True)         # the import runs on the handle's own stream
+        self.d.import_states_device(buf, check=True)         # on the handle's own stream, ordered after torch's (recv, cat)
         self.d.sync()
 
     def rotate_rows(self, rows, turns):

@@ -404,3 +404,34 @@ def test_config5_whole_grid(oq, order, L, oracle_mod, lib):
     w = want[0]
     assert counts[0] == w.nsym and np.array_equal(soft[0, : w.nsym], w.soft) and np.array_equal(bits(symf[0, : w.nsym]), bits(w.sym))
     d1.close()
+
+
+def test_handle_stream_is_ordered_after_torch_stream(lib):
+    """The handle's own stream is non-blocking; process_device orders it after torch's current stream, so buffers
+    torch is still filling (a device copy of the input, the clear of the output) are complete when the kernel runs."""
+    import torch
+    from meteor_demod_b200 import Demod, synth
+    ns, n = 2048, 1 << 16
+    per = synth.baseband(23000, periodic=True, seed=5).astype(np.complex64)
+    src = synth.device_streams(per, ns, n, bps=16, seed=11)
+    want = torch.empty((ns, 2 * 24000), dtype=torch.int8, device="cuda")
+    with Demod(nstreams=ns) as d:
+        d.process_device(src, want)
+        d.sync()
+        cw = d.counts().copy()
+    torch.cuda.synchronize()
+    with Demod(nstreams=ns) as d:
+        junk = torch.full_like(src, 17)
+        for _ in range(3):
+            raw = junk.clone()                               # queue some work in front ...
+        raw = src.clone()                                    # ... of the copy the kernel must wait for
+        got = torch.full((ns, 2 * 24000), 99, dtype=torch.int8, device="cuda")
+        got.zero_()
+        want_clear = torch.zeros_like(want)
+        d.process_device(raw, got)
+        d.sync()
+        cg = d.counts().copy()
+    assert np.array_equal(cw, cg)
+    m = torch.arange(24000, device="cuda")[None, :] < torch.as_tensor(cw.astype(np.int64), device="cuda")[:, None]
+    m2 = m.repeat_interleave(2, dim=1)
+    assert torch.equal(want[m2], got[m2]) and int((got[~m2] != 0).sum()) == 0 and want_clear.sum() == 0

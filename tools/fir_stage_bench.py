@@ -31,9 +31,15 @@ for name, symrate, oq, bps, order, L in (("c1", 72000, 0, 16, 32, 5), ("c2", 800
     raw = synth.device_streams(per, R, N, bps=bps, sps=230000 / symrate, seed=5)
     out = torch.empty((R, N * L * 2), dtype=torch.float32, device="cuda")
     taps = 2 * order + 1
-    for mode, mname in ((0, "exact"), (1, "fma")):
-        best = 1e9
-        for _ in range(4):
+    modes = ((0, "exact"), (1, "fma"))
+    if "--sweep" in sys.argv:                                  # bits 1-2 of mode: samples per thread (0 = by filter length)
+        modes = tuple((m | (ns_ << 1), "%s/ns%d" % (nm, ns_)) for m, nm in modes for ns_ in (1, 2))
+    for mode, mname in modes:
+        best, times = 1e9, []
+        for _ in range(30):                                   # ~0.3 s of launches first: clocks up, code resident
+            lib.lrpt_fir_stage_device(C.byref(p), raw.data_ptr(), raw.stride(0) * raw.element_size(), R, N,
+                                      out.data_ptr(), out.stride(0) * 4, mode, None)
+        for _ in range(10):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
@@ -42,18 +48,20 @@ for name, symrate, oq, bps, order, L in (("c1", 72000, 0, 16, 32, 5), ("c2", 800
             e1.record()
             torch.cuda.synchronize()
             assert rc == 0, rc
-            best = min(best, e0.elapsed_time(e1))
+            times.append(e0.elapsed_time(e1))
+        best = float(np.median(times))
         ns = R * N
         gbs = ns * (bps // 4 + 8 * L) / (best * 1e-3) / 1e9
         tf = ns * 4.0 * taps * L / (best * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        row = {"config": name, "mode": mname, "taps": taps, "interp": L, "bps": bps, "samples": ns, "ms": best,
+        row = {"config": name, "mode": mname, "taps": taps, "interp": L, "bps": bps, "samples": ns, "ms": best, "ms_min": min(times), "ms_max": max(times),
                "gsps": ns / best / 1e6, "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / peak, "fp32_tflops": tf,
                "fp32_flop_frac_of_75TF": tf / fp32_peak,
-               "fp32_pipe_frac_est": tf / fp32_peak * (2.0 if mode == 0 else 1.0),
+               "fp32_pipe_frac_est": tf / fp32_peak * (1.0 if mode & 1 else 2.0),
                "bytes_per_sample": bps // 4 + 8 * L, "flops_per_sample": 4 * taps * L}
         rows_out.append(row)
         print(json.dumps(row), flush=True)
     del raw, out
     torch.cuda.empty_cache()
-json.dump({"hbm_peak_gbs": peak, "rows": rows_out}, open(os.path.join(ROOT, "gpurun_out", "r2_fir_stage.json"), "w"), indent=1)
+name = "r2_fir_stage_sweep.json" if "--sweep" in sys.argv else "r2_fir_stage.json"
+json.dump({"hbm_peak_gbs": peak, "rows": rows_out}, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
