@@ -12,10 +12,12 @@
  *                       symmetries of the constellation (4 quarter turns x I/Q swap) -> best score, symmetry
  *   fe_peak_kernel      first maximum per window of one CADU
  *   fe_viterbi_kernel   one warp per CADU, persistent over the frame list: lane l holds the path metrics of
- *                       states l and l + 32; the butterfly's operands come from lanes l>>1 and 16 + (l>>1) by
- *                       shuffles, branch metrics are +-I +-Q with per-lane signs fixed at start, decisions leave as
- *                       two ballots per step into an L2-resident scratch ring, traceback walks it backwards 32 steps
- *                       at a time (one coalesced load per batch, the words handed round by shuffles).
+ *                       states l and l + 32 as two 16-bit fields of one register; the butterfly's operands come
+ *                       from lanes l>>1 and 16 + (l>>1) by two shuffles, the branch metrics of both states are one
+ *                       packed integer I*cI + Q*cQ with per-lane constants, add-compare-select of both states is
+ *                       two adds and one VIMNMX.S16x2 (DPX); a lane keeps the decisions of its own two states for
+ *                       32 steps in two registers and writes them coalesced into a scratch ring; traceback walks
+ *                       it backwards 32 steps at a time with one shuffle per step and stores four bytes per batch.
  *
  * Byte / integer work, HBM-bound for the synchroniser (2 bytes read and 2 written per symbol) and latency-bound
  * per frame for the decoder (8320 dependent add-compare-select steps), which is why it runs one warp per frame
@@ -31,7 +33,7 @@ constexpr int FE_G1 = 0x4F, FE_G2 = 0x6D;
 constexpr int FE_CADU = 1024, FE_CADU_SYMS = 8192, FE_HEAD = 64, FE_TAIL = 64;
 constexpr int FE_STEPS = FE_HEAD + FE_CADU_SYMS + FE_TAIL;
 
-__constant__ unsigned long long c_pat[8];
+struct SyncPatterns { unsigned long long v[8]; };   /* the encoded ASM under the 8 symmetries: a kernel argument (constant bank) */
 
 __host__ __device__ inline int parity7(unsigned x) { x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return (int)(x & 1u); }
 
@@ -79,7 +81,8 @@ __global__ void fe_pack_kernel(const int8_t *__restrict__ soft, size_t nsym, uin
 }
 
 /* four offsets per thread: score/hyp bytes leave as one 32-bit store each */
-__global__ void fe_score_kernel(const uint32_t *__restrict__ words, size_t nsym, uint32_t *__restrict__ score4, uint32_t *__restrict__ hyp4)
+__global__ void fe_score_kernel(const uint32_t *__restrict__ words, size_t nsym, uint32_t *__restrict__ score4, uint32_t *__restrict__ hyp4,
+                                const SyncPatterns pat)
 {
 	const size_t q = (size_t)blockIdx.x*blockDim.x + threadIdx.x;   /* offsets 4q .. 4q+3 */
 	if (4*q >= nsym) return;
@@ -94,7 +97,7 @@ __global__ void fe_score_kernel(const uint32_t *__restrict__ words, size_t nsym,
 		int best = -1, bh = 0;
 #pragma unroll
 		for (int h = 0; h < 8; h++) {
-			const int s = 64 - __popcll(win ^ c_pat[h]);
+			const int s = 64 - __popcll(win ^ pat.v[h]);
 			if (s > best) { best = s; bh = h; }
 		}
 		if (o + 32 > nsym) { best = 0; bh = 0; }                    /* fewer than 32 symbols left: no window */
@@ -135,29 +138,36 @@ __device__ __forceinline__ void unturn(int h, int i, int q, int &oi, int &oq)
 	oi = i; oq = q;
 }
 
+/*
+ * Path metrics travel as two signed 16-bit fields of one register, P = pm[lane] | pm[lane + 32] << 16, so that one
+ * shuffle moves two metrics and one VIMNMX.S16x2 (the DPX max with per-field predicates) does the compare-select of
+ * both states of a lane. Every field stays inside [0, 32767] -- then the packed fields add and subtract as one
+ * 32-bit integer without borrows between them: the metrics of the 64 states of this code never differ by more than
+ * 12 branch metrics (any state is reached from any other in K - 1 = 6 steps; |branch metric| <= 256) = 3072, and at
+ * the start of every batch of 32 steps the smallest is moved to 8192 (it can fall by 256 a step), the moved amount
+ * kept in `base`. Decisions depend on metric differences only, so they are the oracle's (32-bit metrics, no
+ * normalisation) bit for bit, and field + base is its metric.
+ */
+static_assert(FE_STEPS % 32 == 0, "the scratch ring holds whole batches");
+static_assert((FE_G1 & 0x40) && (FE_G2 & 0x40), "both generators tap the oldest bit: the two branches into a state carry opposite symbols");
+constexpr int FE_BIAS = 8192;
+
 __global__ void __launch_bounds__(128)
 fe_viterbi_kernel(const int8_t *__restrict__ soft, size_t nsym, const uint32_t *__restrict__ frame_off, const uint8_t *__restrict__ frame_hyp,
                   int nframes, uint8_t *__restrict__ cadu, int32_t *__restrict__ metric, uint2 *__restrict__ scratch)
 {
-	const int lane = threadIdx.x & 31;
+	__shared__ __align__(16) int2 s_sym[4][32];                         /* per warp: (I, Q) of the 32 steps of a batch, symmetry undone */
+	const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
 	const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
 	const int nwarps = (gridDim.x*blockDim.x) >> 5;
-	uint2 *dec = scratch + (size_t)warp*FE_STEPS;                       /* this warp's decision words, one per step */
+	uint2 *dec = scratch + (size_t)warp*FE_STEPS;                       /* decision words: [batch][lane] = 32 steps of states lane, lane + 32 */
 
-	/* state lane (low) and lane + 32 (high); both are entered by input bit b = lane & 1 from predecessors
-	 * p0 = s >> 1 (older bit 0) and p1 = p0 | 32. Signs of the branch metric (c ? +r : -r), fixed per lane. */
-	const int b = lane & 1;
-	int sgn[2][2][2];                                                   /* [state low/high][pred 0/1][I/Q] */
-#pragma unroll
-	for (int hs = 0; hs < 2; hs++) {
-		const int s = lane + 32*hs;
-#pragma unroll
-		for (int p = 0; p < 2; p++) {
-			const unsigned r = (unsigned)((((s >> 1) | (p ? 32 : 0)) << 1) | b);
-			sgn[hs][p][0] = parity7(r & FE_G1) ? 1 : -1;
-			sgn[hs][p][1] = parity7(r & FE_G2) ? 1 : -1;
-		}
-	}
+	/* Lane l holds states l (low field) and l + 32 (high field). Both are entered by input bit b = l & 1 from
+	 * p0 = s >> 1 (older bit 0) and p1 = p0 | 32; the encoder register of the p0 branch is (p0 << 1) | b = s itself,
+	 * the p1 branch carries the opposite symbol pair. Branch metric of the p0 branch: sI*I + sQ*Q. */
+	const int sI_lo = parity7((unsigned)lane & FE_G1) ? 1 : -1, sQ_lo = parity7((unsigned)lane & FE_G2) ? 1 : -1;
+	const int sI_hi = parity7((unsigned)(lane + 32) & FE_G1) ? 1 : -1, sQ_hi = parity7((unsigned)(lane + 32) & FE_G2) ? 1 : -1;
+	const int cI = sI_lo + sI_hi*65536, cQ = sQ_lo + sQ_hi*65536;       /* bm_lo + 65536*bm_hi = I*cI + Q*cQ */
 	const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);           /* lanes holding the predecessors' metrics */
 
 	for (int f = warp; f < nframes; f += nwarps) {
@@ -166,33 +176,57 @@ fe_viterbi_kernel(const int8_t *__restrict__ soft, size_t nsym, const uint32_t *
 		const long long lo = start - FE_HEAD < 0 ? 0 : start - FE_HEAD;
 		const long long hi = start + FE_CADU_SYMS + FE_TAIL > (long long)nsym ? (long long)nsym : start + FE_CADU_SYMS + FE_TAIL;
 		const int n = (int)(hi - lo);
-		int A = 0, B = 0;                                               /* pm[lane], pm[lane + 32] */
+		unsigned P = (unsigned)FE_BIAS*65537u;                          /* all metrics 0 */
+		int base = -FE_BIAS;
 		const char2 *sym = reinterpret_cast<const char2 *>(soft) + lo;
-		/* forward pass, 32 steps per batch: lane j fetches the symbol of step t0 + j (one coalesced load) */
+
+		/* one add-compare-select step of both states of the lane; the survivor bits ("came from p0") shift into acc */
+#define FE_ACS(ri, rq) do { \
+			const unsigned v0 = __shfl_sync(0xffffffffu, P, src_lo), v1 = __shfl_sync(0xffffffffu, P, src_hi); \
+			const unsigned bm = (unsigned)((ri)*cI + (rq)*cQ); \
+			const unsigned l0 = __byte_perm(v0, v1, 0x5410) + bm;       /* pm[p0] + bm, fields (low state, high state) */ \
+			const unsigned l1 = __byte_perm(v0, v1, 0x7632) - bm;       /* pm[p1] - bm */ \
+			bool keep_hi, keep_lo;                                      /* l0 >= l1: ties to the predecessor with the older bit 0 */ \
+			P = __vibmax_s16x2(l0, l1, &keep_hi, &keep_lo); \
+			acc_lo = (acc_lo << 1) | (keep_lo ? 1u : 0u); acc_hi = (acc_hi << 1) | (keep_hi ? 1u : 0u); \
+		} while (0)
+
 		for (int t0 = 0; t0 < n; t0 += 32) {
 			char2 mine = make_char2(0, 0);
-			if (t0 + lane < n) mine = sym[t0 + lane];
+			if (t0 + lane < n) mine = sym[t0 + lane];                   /* one coalesced load per batch */
 			int mi, mq;
 			unturn(h, mine.x, mine.y, mi, mq);
-			const int steps = min(32, n - t0);
-			uint32_t d_lo_mine = 0, d_hi_mine = 0;                      /* decisions of step t0 + lane */
-			for (int j = 0; j < steps; j++) {
-				const int ri = __shfl_sync(0xffffffffu, mi, j), rq = __shfl_sync(0xffffffffu, mq, j);
-				const int a0 = __shfl_sync(0xffffffffu, A, src_lo), b0 = __shfl_sync(0xffffffffu, B, src_lo);
-				const int a1 = __shfl_sync(0xffffffffu, A, src_hi), b1 = __shfl_sync(0xffffffffu, B, src_hi);
-				/* low state: predecessors pm[lane>>1] (= A of src_lo) and pm[(lane>>1)+32] (= B of src_lo) */
-				const int l0 = a0 + sgn[0][0][0]*ri + sgn[0][0][1]*rq;
-				const int l1 = b0 + sgn[0][1][0]*ri + sgn[0][1][1]*rq;
-				const int h0 = a1 + sgn[1][0][0]*ri + sgn[1][0][1]*rq;
-				const int h1 = b1 + sgn[1][1][0]*ri + sgn[1][1][1]*rq;
-				const bool dl = l1 > l0, dh = h1 > h0;                  /* ties to the predecessor with the older bit 0 */
-				A = dl ? l1 : l0; B = dh ? h1 : h0;
-				const uint32_t wl = __ballot_sync(0xffffffffu, dl), wh = __ballot_sync(0xffffffffu, dh);
-				if (lane == j) { d_lo_mine = wl; d_hi_mine = wh; }
+			s_sym[wq][lane] = make_int2(mi, mq);
+			/* smallest metric back to FE_BIAS */
+			unsigned m = P;
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) m = __vmins2(m, __shfl_xor_sync(0xffffffffu, m, d));
+			{
+				const int f0 = (int)(m & 0xffffu), f1 = (int)(m >> 16);
+				const int delta = (f0 < f1 ? f0 : f1) - FE_BIAS;
+				P -= (unsigned)delta*65537u; base += delta;
 			}
-			if (t0 + lane < n) dec[t0 + lane] = make_uint2(d_lo_mine, d_hi_mine);   /* coalesced: 256 bytes per batch */
+			__syncwarp();
+			const int steps = min(32, n - t0);
+			unsigned acc_lo = 0, acc_hi = 0;
+			if (steps == 32) {
+#pragma unroll
+				for (int j = 0; j < 32; j += 2) {
+					const int4 r = *reinterpret_cast<const int4 *>(&s_sym[wq][j]);   /* two steps per broadcast load */
+					FE_ACS(r.x, r.y);
+					FE_ACS(r.z, r.w);
+				}
+			} else {
+				for (int j = 0; j < steps; j++) { const int2 r = s_sym[wq][j]; FE_ACS(r.x, r.y); }
+				acc_lo <<= 32 - steps; acc_hi <<= 32 - steps;
+			}
+			/* decision bit = 1 when the survivor came from p1; step j of the batch at bit 31 - j */
+			dec[t0 + lane] = make_uint2(~acc_lo, ~acc_hi);              /* coalesced: 256 bytes per batch */
+			__syncwarp();                                               /* s_sym is rewritten by the next batch */
 		}
+#undef FE_ACS
 		/* best end state: highest metric, lowest state on ties */
+		const int A = (int)(P & 0xffffu) + base, B = (int)(P >> 16) + base;
 		long long key = (long long)A*256 + (63 - lane);
 		{
 			const long long kb = (long long)B*256 + (63 - (lane + 32));
@@ -202,28 +236,42 @@ fe_viterbi_kernel(const int8_t *__restrict__ soft, size_t nsym, const uint32_t *
 		int s = 63 - (int)(key & 0xff);
 		if (lane == 0 && metric) metric[f] = (int32_t)((key - (key & 0xff))/256);
 		__syncwarp();
-		/* traceback, 32 steps per batch, newest first; every lane follows the state, lane k collects byte k's bits */
+		/* traceback, 32 steps per batch, newest first. Every lane follows the state; the decision of state s at a step
+		 * sits in lane s & 31 (field s >> 5): one shuffle per step. */
 		uint8_t *out = cadu + (size_t)f*FE_CADU;
 		for (int i = lane; i < FE_CADU/4; i += 32) reinterpret_cast<uint32_t *>(out)[i] = 0u;
 		__syncwarp();
+		const bool word_aligned = ((lo - start) & 31) == 0;             /* a batch = four whole bytes of the frame */
 		const int nb = (n + 31)/32;
 		for (int bt = nb - 1; bt >= 0; bt--) {
 			const int t0 = 32*bt;
-			uint2 w = make_uint2(0u, 0u);
-			if (t0 + lane < n) w = dec[t0 + lane];
+			const uint2 w = dec[t0 + lane];                             /* a word per STATE pair: all 32 lanes, also in a short batch */
 			const int steps = min(32, n - t0);
 			uint32_t bits = 0;                                          /* decoded input bits of this batch, step j in bit j */
-			for (int j = steps - 1; j >= 0; j--) {
-				const uint32_t wl = __shfl_sync(0xffffffffu, w.x, j), wh = __shfl_sync(0xffffffffu, w.y, j);
-				bits |= (uint32_t)(s & 1) << j;
-				const uint32_t d = (s < 32 ? (wl >> s) : (wh >> (s - 32))) & 1u;
-				s = (s >> 1) | (d ? 32 : 0);
+#define FE_BACK(k) do { \
+				const unsigned c = ((w.x >> (k)) & 1u) | (((w.y >> (k)) & 1u) << 1); \
+				const unsigned v = __shfl_sync(0xffffffffu, c, s & 31); \
+				bits = (bits << 1) | (unsigned)(s & 1); \
+				s = (s >> 1) | (int)(((v >> (s >> 5)) & 1u) << 5); \
+			} while (0)
+			if (steps == 32) {
+#pragma unroll
+				for (int k = 0; k < 32; k++) FE_BACK(k);                /* step j = 31 - k */
+			} else {
+				for (int j = steps - 1; j >= 0; j--) FE_BACK(31 - j);
 			}
-			/* steps t0 .. t0+31 are frame symbols lo + t - start; lane 0 writes the four bytes they cover */
+#undef FE_BACK
 			if (lane == 0) {
-				for (int j = 0; j < steps; j++) {
-					const long long symi = lo + t0 + j - start;
-					if (symi >= 0 && symi < FE_CADU_SYMS && ((bits >> j) & 1u)) out[symi >> 3] |= (uint8_t)(0x80u >> (symi & 7));
+				const long long sym0 = lo + t0 - start;                 /* frame symbol of step 0 of the batch */
+				if (word_aligned && steps == 32) {
+					/* symbol sym0 + j is bit 7 - (j & 7) of byte (sym0 + j) >> 3: reverse the bits, then the bytes */
+					if (sym0 >= 0 && sym0 < FE_CADU_SYMS)
+						*reinterpret_cast<uint32_t *>(out + (sym0 >> 3)) = __byte_perm(__brev(bits), 0u, 0x0123);
+				} else {
+					for (int j = 0; j < steps; j++) {
+						const long long symi = sym0 + j;
+						if (symi >= 0 && symi < FE_CADU_SYMS && ((bits >> j) & 1u)) out[symi >> 3] |= (uint8_t)(0x80u >> (symi & 7));
+					}
 				}
 			}
 		}
@@ -233,26 +281,19 @@ fe_viterbi_kernel(const int8_t *__restrict__ soft, size_t nsym, const uint32_t *
 
 } // namespace
 
-#define FE_CK(x) do { if ((x) != cudaSuccess) return LRPT_ERR_CUDA; } while (0)
-
 extern "C" int lrpt_fe_sync_device(const int8_t *d_soft, size_t nsym, uint8_t *d_score, uint8_t *d_hyp, uint32_t *d_words,
                                    void *cuda_stream)
 {
 	if (!d_soft || !d_score || !d_hyp || !d_words || nsym < 32 || nsym > ((size_t)1 << 32) - 64) return LRPT_ERR_ARG;
 	if (((uintptr_t)d_soft & 15) || ((uintptr_t)d_score & 3) || ((uintptr_t)d_hyp & 3)) return LRPT_ERR_ARG;
-	static bool have_pat = false;
 	cudaStream_t st = (cudaStream_t)cuda_stream;
-	{
-		unsigned long long pat[8];
-		for (int h = 0; h < 8; h++) pat[h] = sync_pattern(h);
-		FE_CK(cudaMemcpyToSymbolAsync(c_pat, pat, sizeof(pat), 0, cudaMemcpyHostToDevice, st));   /* per device, cheap */
-		have_pat = true; (void)have_pat;
-	}
+	SyncPatterns pat;
+	for (int h = 0; h < 8; h++) pat.v[h] = sync_pattern(h);
 	const size_t nwords = (nsym + 15)/16 + 2;
 	fe_pack_kernel<<<(unsigned)((nwords + 255)/256), 256, 0, st>>>(d_soft, nsym, d_words, nwords);
 	const size_t nq = (nsym + 3)/4;
 	fe_score_kernel<<<(unsigned)((nq + 255)/256), 256, 0, st>>>(d_words, nsym, reinterpret_cast<uint32_t *>(d_score),
-	                                                          reinterpret_cast<uint32_t *>(d_hyp));
+	                                                          reinterpret_cast<uint32_t *>(d_hyp), pat);
 	return cudaGetLastError() == cudaSuccess ? LRPT_OK : LRPT_ERR_CUDA;
 }
 
@@ -272,7 +313,7 @@ extern "C" size_t lrpt_fe_viterbi_scratch_bytes(int device)
 {
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-	return (size_t)sms*8*4*FE_STEPS*sizeof(uint2);                     /* 8 CTAs of 4 warps per SM */
+	return (size_t)sms*16*4*FE_STEPS*sizeof(uint2);                    /* 16 CTAs of 4 warps per SM */
 }
 
 extern "C" int lrpt_fe_viterbi_device(const int8_t *d_soft, size_t nsym, const uint32_t *d_frame_off, const uint8_t *d_frame_hyp,

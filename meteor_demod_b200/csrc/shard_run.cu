@@ -148,6 +148,9 @@ constexpr int NCCL_CHAR = 0;                                    /* ncclInt8 / nc
 struct Shared {
 	int world = 1;
 	pthread_barrier_t bar;
+	pthread_mutex_t gate_mu = PTHREAD_MUTEX_INITIALIZER;        /* start gate: 0 = wait, 1 = go, -1 = a thread could not be created */
+	pthread_cond_t gate_cv = PTHREAD_COND_INITIALIZER;
+	int gate = 0;
 	std::vector<int> rc, ksum, ksum2, aligned, launches;
 	std::vector<float> agree_scan, agree_final;
 	std::vector<long long> nsym_rank, first_lock_rank;          /* symbols a rank contributes; its first locked output symbol (-1) */
@@ -538,7 +541,16 @@ struct Rank {
 	}
 };
 
-void *rank_main(void *arg) { static_cast<Rank *>(arg)->run(); return nullptr; }
+void *rank_main(void *arg)
+{
+	Rank *r = static_cast<Rank *>(arg);
+	pthread_mutex_lock(&r->sh->gate_mu);
+	while (!r->sh->gate) pthread_cond_wait(&r->sh->gate_cv, &r->sh->gate_mu);
+	const int go = r->sh->gate;
+	pthread_mutex_unlock(&r->sh->gate_mu);
+	if (go > 0) r->run();
+	return nullptr;
+}
 
 } // namespace
 
@@ -596,11 +608,18 @@ extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrp
 		ranks[i].job = Job{ params, plan, static_cast<const uint8_t *>(raw_iq), nsamples, soft, cap, M };
 		ranks[i].sh = &sh; ranks[i].rank = i; ranks[i].dev = devices ? devices[i] : params->device;
 	}
-	for (int i = 1; i < world; i++) pthread_create(&tids[i], nullptr, rank_main, &ranks[i]);
-	ranks[0].run();
-	for (int i = 1; i < world; i++) pthread_join(tids[i], nullptr);
+	/* the ranks meet at barriers sized for `world`: nobody starts before every thread exists */
+	int started = 1;
+	for (int i = 1; i < world; i++, started++) if (pthread_create(&tids[i], nullptr, rank_main, &ranks[i])) break;
+	pthread_mutex_lock(&sh.gate_mu);
+	sh.gate = started == world ? 1 : -1;
+	pthread_cond_broadcast(&sh.gate_cv);
+	pthread_mutex_unlock(&sh.gate_mu);
+	if (started == world) ranks[0].run();
+	for (int i = 1; i < started; i++) pthread_join(tids[i], nullptr);
 	pthread_barrier_destroy(&sh.bar);
 	if (world > 1) for (int i = 0; i < world; i++) if (sh.comms[i]) nccl.CommDestroy(sh.comms[i]);
+	if (started != world) return LRPT_ERR_NOMEM;
 	for (int i = 0; i < world; i++) if (sh.rc[i]) return sh.rc[i];
 
 	long long total = 0, lock = sh.head_lock;

@@ -98,10 +98,19 @@ def test_gpu_viterbi_equals_oracle(lib, oracle_mod):
         if k < 5:
             errors += int(np.unpackbits(want[4:] ^ frames[k]).sum())
     assert 0 < errors < 4000                                   # the channel is bad enough to exercise ties and wrong paths
+    # full-scale input (every soft value -128 or 127, no code structure): the widest metric spread and the fastest
+    # drift the packed 16-bit metrics of the kernel have to hold
+    ext = np.random.default_rng(31).choice(np.array([-128, 127], dtype=np.int8), size=(3 * fe.CADU_SYMS, 2))
+    eo, eh = [0, 100, 4096, 8192 + 31, 2 * 8192], [0, 1, 2, 7, 5]
+    c2, m2 = vit.decode(torch.from_numpy(ext).cuda(), torch.tensor(eo, dtype=torch.int32, device="cuda"),
+                        torch.tensor(eh, dtype=torch.uint8, device="cuda"))
+    for k, (o, h) in enumerate(zip(eo, eh)):
+        want, wm = fe.viterbi_cadu(ext, o, h)
+        assert np.array_equal(c2[k].cpu().numpy(), want) and int(m2[k]) == wm, (k, o, h)
     # many frames: more frames than resident warps, decoded in several rounds
-    reps = torch.tensor(offs[:5] * 400, dtype=torch.int32, device="cuda")
-    many, _ = vit.decode(d_soft, reps, torch.full((2000,), 6, dtype=torch.uint8, device="cuda"))
-    assert torch.equal(many.view(400, 5, 1024), many[:5].unsqueeze(0).expand(400, 5, 1024))
+    reps = torch.tensor(offs[:5] * 2400, dtype=torch.int32, device="cuda")
+    many, _ = vit.decode(d_soft, reps, torch.full((12000,), 6, dtype=torch.uint8, device="cuda"))
+    assert torch.equal(many.view(2400, 5, 1024), many[:5].unsqueeze(0).expand(2400, 5, 1024))
 
 
 @pytest.mark.gpu
