@@ -69,12 +69,14 @@ def parse():
                     help="sharded: chunks continue from their predecessor's state (sharded.run_handoff; the default)")
     ap.add_argument("--seed-carrier", action="store_true", help="sharded: chunks >= 1 start their Costas NCO at a coarse "
                     "carrier estimate (meteor_demod_b200/acquire.py; opt-in, not what the reference does)")
+    ap.add_argument("--seed-nfft", type=int, default=1 << 17, help="sharded: samples the coarse carrier estimate looks at")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-locked", action="store_true", help="skip the steady-state (locked, state carried over) pass")
     ap.add_argument("--no-single", action="store_true", help="skip the single exact stream sub-record")
     ap.add_argument("--no-frontend", action="store_true", help="skip the decoder front-end sub-record")
     ap.add_argument("--no-c4", action="store_true", help="skip the time-sharded single-stream sub-record (BASELINE config 4)")
     ap.add_argument("--c4-samples", type=int, default=1 << 33, help="length of the ONE stream of the c4 sub-record")
+    ap.add_argument("--c4-unseeded", action="store_true", help="c4 with the reference's own acquisition sweep in every chunk (150 k warm-up)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target CPU work per core for the baseline")
     return ap.parse_args()
@@ -434,7 +436,8 @@ def main():
             raw.copy_(h_raw, non_blocking=True)
             ev1.record(s_in)
         with torch.cuda.stream(s_out):
-            h_soft[:, : 2 * nsym_max].copy_(soft[:, : 2 * nsym_max], non_blocking=True)
+            nb_out = B * 2 * nsym_max                           # the bytes a step returns, as ONE contiguous copy
+            h_soft.view(-1)[:nb_out].copy_(soft.view(-1)[:nb_out], non_blocking=True)
             ev2.record(s_out)
         torch.cuda.synchronize()
         tl = torch.tensor([max(ev0.elapsed_time(ev1), ev0.elapsed_time(ev2)), ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
@@ -526,19 +529,31 @@ def main():
         front = bench_frontend(local, rank)
 
     # ---- c4: BASELINE config 4 -- ONE long stream, time-sharded over chunks and ranks with state hand-off ------
-    c4 = None
+    c4 = c4_weak = None
     if not a.no_c4:
-        a_c4 = argparse.Namespace(**vars(a))
-        a_c4.stream_samples, a_c4.steps, a_c4.warmup = a.c4_samples, max(1, min(a.steps, 3)), 1
-        a_c4.two_pass = a_c4.single_pass = a_c4.seed_carrier = False
-        a_c4.warm = 0
-        c4, sd_, raw_, res_ = sharded_measure(a_c4, cfg, label, rank, world, local)
-        sd_.close()
-        del sd_, raw_, res_
-        torch.cuda.empty_cache()
-        if c4 is not None:
-            c4 = {k: c4[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches", "symbols_per_step",
-                                      "min_boundary_agreement", "tier_s", "phase_ms", "kernel", "chunks_per_rank")}
+        def c4_record(nsamples, scaling):
+            a_c4 = argparse.Namespace(**vars(a))
+            a_c4.stream_samples, a_c4.steps, a_c4.warmup = nsamples, max(1, min(a.steps, 3)), 1
+            a_c4.two_pass = a_c4.single_pass = False
+            # chunks >= 1 start their Costas NCO at a coarse carrier estimate instead of sweeping to the carrier
+            # at 1e-6 rad/symbol^2 (pll.c:126): 32 Ki samples of warm-up instead of 150 k; chunk 0 stays the sequential run
+            a_c4.seed_carrier, a_c4.seed_nfft, a_c4.warm = (not a.c4_unseeded), 4096, (150000 if a.c4_unseeded else 32768)
+            rec, sd_, raw_, res_ = sharded_measure(a_c4, cfg, label, rank, world, local)
+            sd_.close()
+            sd_.eng.raw = None
+            del sd_, raw_, res_
+            torch.cuda.empty_cache()
+            if rec is not None:
+                rec = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches", "symbols_per_step",
+                                           "min_boundary_agreement", "tier_s", "phase_ms", "phase_ms_per_rank", "kernel", "chunks_per_rank")}
+                rec["scaling"] = scaling
+                rec["stream_samples"] = int(nsamples)
+            return rec
+        c4 = c4_record(a.c4_samples, "strong")
+        if world > 1:
+            # the same path with the recording growing with the ranks (every rank keeps the N = 1 share): what the
+            # per-lane latency floor of the strong-scaling record hides
+            c4_weak = c4_record(a.c4_samples * world, "weak")
 
     if rank != 0:
         if world > 1:
@@ -579,7 +594,7 @@ def main():
                          "note": "instruction-issue bound, not HBM bound (DESIGN.md section 5); the reference's own lazy "
                                  "FIR (4*taps flops per filter_get) runs at %.2f Tflop/s" % (fir_flops / (kern_ms * 1e-3) / 1e12),
                          "limiter": limiter},
-            "e2e": e2e, "value_locked": locked, "single_stream": single, "c4": c4, "frontend": front,
+            "e2e": e2e, "value_locked": locked, "single_stream": single, "c4": c4, "c4_weak": c4_weak, "frontend": front,
             "host_cores_bound_to_gpu_numa_node": numa}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
@@ -747,7 +762,7 @@ def sharded_measure(a, cfg, label, rank, world, local):
     raw = synth.device_long_stream(period, N, total=span, bps=bps, sps=FS / symrate, first=s0)
     kw = dict(chunk=a.chunk, warm=a.warm, overlap=8192, device=local, dist=dist if world > 1 else None, raw_first=s0,
               symrate=symrate, bps=bps, rrc_order=order, interp_factor=interp, two_pass=not a.single_pass,
-              handoff=a.handoff, seed_carrier=a.seed_carrier, oqpsk=bool(oqpsk))
+              handoff=a.handoff, seed_carrier=a.seed_carrier, seed_nfft=a.seed_nfft, oqpsk=bool(oqpsk))
 
     def barrier():
         torch.cuda.synchronize()
@@ -817,8 +832,12 @@ def sharded_measure(a, cfg, label, rank, world, local):
     else:
         allr = [mine]
     ph_t = torch.tensor([phases.get(k, 0.0) / max(1, a.steps) for k in PHASES], dtype=torch.float64, device="cuda")
+    ph_all = [torch.zeros_like(ph_t) for _ in range(world)]
     if world > 1:
+        dist.all_gather(ph_all, ph_t)
         dist.all_reduce(ph_t, op=dist.ReduceOp.MAX)
+    else:
+        ph_all = [ph_t.clone()]
     line = None
     if rank == 0:
         per_rank = [{"rank": r, "symbols": int(v[0].item()), "frac_gt_1lsb": float(v[1].item()),
@@ -842,7 +861,8 @@ def sharded_measure(a, cfg, label, rank, world, local):
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "%s; ONE stream of %d samples time-sharded: %d chunks of %d, warm-up %d, overlap 8192, %s"
-                           % (label, N, plan.nchunks, a.chunk, a.warm, "state hand-off between chunks and ranks" if a.handoff else "single pass" if a.single_pass else "two-pass lock-point alignment"),
+                           % (label, N, plan.nchunks, a.chunk, a.warm, ("state hand-off between chunks and ranks" if a.handoff else "single pass" if a.single_pass else "two-pass lock-point alignment")
+                              + ("; chunks >= 1 start at a coarse carrier estimate (x^4 line, %d-point FFT) instead of the reference's sweep" % a.seed_nfft if a.seed_carrier else "")),
                            "parity": "Tier-S (statistical): chunks 0 and 1 bit-exact, later chunks see tier_s",
                            "l2": "stream (%.1f GB, %.1f GB resident per rank) larger than L2" % (N * (bps // 4) / 1e9, span * (bps // 4) / 1e9)},
                 "gpu_launches": int(launches), "symbols_per_step": int(nsym.item()),
@@ -850,6 +870,7 @@ def sharded_measure(a, cfg, label, rank, world, local):
                 "tier_s": {"frac_gt_1lsb": worst, "per_rank": per_rank,
                            "reference_fma_vs_strict": ref_eps},
                 "phase_ms": dict(zip(PHASES, [float(v) for v in ph_t.tolist()])),
+                "phase_ms_per_rank": [[round(float(v), 2) for v in t_.tolist()] for t_ in ph_all],
                 "kernel": sd.eng.d.kernel_name(), "chunks_per_rank": int(c1 - c0), "clocks": clk.summary()}
     return line, sd, raw, res
 

@@ -94,6 +94,12 @@ class Plan:
         at B_c; a symbol instant falling exactly on B_c is in one row and not the other)."""
         return (self.boundary(c) + self.cut_shift + min(64, self.overlap // 4)) * self.interp
 
+    def cut_targets(self, c0, c1, device=None):
+        """cut_target(c) for c in [c0, c1), c0 >= 1, as an int64 tensor (no Python loop: a long stream has 1e5 chunks)."""
+        assert c0 >= 1
+        c = torch.arange(c0, c1, dtype=torch.int64, device=device)
+        return (self.warm + c * self.chunk + self.cut_shift + min(64, self.overlap // 4)) * self.interp
+
     @property
     def n_main(self):              # samples up to the successor's boundary
         return self.warm + self.chunk
@@ -288,7 +294,7 @@ def stitch(soft, q, count, plan, first_chunk=0, dist=None, base=None, oqpsk_half
     world = dist.get_world_size() if dist is not None else 1
     M, L, dev = soft.shape[0], plan.interp, soft.device
     big = torch.iinfo(torch.int64).max
-    Bq = torch.tensor([plan.cut_target(first_chunk + c) for c in range(1, M)], dtype=torch.int64, device=dev)
+    Bq = plan.cut_targets(first_chunk + 1, first_chunk + M, dev)
     if oqpsk_half is not None:
         k, agree, cut = boundary_quadrants_oqpsk(soft, q if base is None else q.to(torch.int64) + base[:, None],
                                                  count, Bq, oqpsk_half)
@@ -408,7 +414,8 @@ def chunk_turns(res, M):
 class GpuEngine:
     """Chunks of one device-resident raw stream through liblrpt_b200.so, one recurrence lane each."""
 
-    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, raw_first=0, seed_carrier=False, **cfg):
+    def __init__(self, raw, plan, device=0, first_chunk=0, nchunks=None, raw_first=0, seed_carrier=False, seed_nfft=1 << 17,
+                 **cfg):
         """raw: device tensor of the raw dtype whose item 0 is I of stream sample `raw_first` -- the whole
         (padded) stream, or just the span this engine's chunks read: [plan.start(first_chunk),
         plan.start(last chunk) + n_main + 2*overlap). seed_carrier (opt-in, not what the reference does): every
@@ -417,7 +424,7 @@ class GpuEngine:
         from .demod import Demod
         self.plan, self.raw, self.first, self.raw_first = plan, raw, first_chunk, raw_first
         self.oqpsk = bool(cfg.get("oqpsk"))
-        self.seed = bool(seed_carrier)
+        self.seed, self.seed_nfft = bool(seed_carrier), int(seed_nfft)
         self.M = plan.nchunks - first_chunk if nchunks is None else nchunks
         self.d = Demod(nstreams=self.M, device=device, interp_factor=plan.interp, **cfg)
         n_all = plan.n_main + plan.overlap
@@ -455,7 +462,7 @@ class GpuEngine:
         W = self.plan.warm
         self.d.reset()
         if self.seed:
-            self.seed_carrier()
+            self.seed_carrier(nfft=self.seed_nfft)
         if W:
             self.d.process_device(self._view(0, W), self.soft, nsym=self.nsym, nsamples=W)
         self.d.sync()
@@ -473,13 +480,16 @@ class GpuEngine:
         self.d.sync()
         return self._result(p.warm)
 
-    def seed_carrier(self, nfft=1 << 17, group=1024):
+    def seed_carrier(self, nfft=1 << 17, group=None):
         """Rows of chunks >= 1: p_freq = the NCO step of a coarse carrier estimate over the row's first nfft samples
-        (everything else stays power-on). Chunk 0 is left alone: the head of the stream is the sequential run."""
+        (everything else stays power-on). Chunk 0 is left alone: the head of the stream is the sequential run.
+        `group` rows go through the estimator at a time (default: 2^25 samples per batch of torch ops)."""
         from . import acquire
         from ._lib import State
         par = self.d.p
         nfft = min(nfft, self.plan.n_main)
+        if group is None:
+            group = max(64, (1 << 25) // nfft)
         rows = self.export_rows()
         off = State.p_freq.offset
         for r0 in range(0, self.M, group):
@@ -659,7 +669,7 @@ class ShardedDemod:
     are built once; run() can be called repeatedly, e.g. by bench.py)."""
 
     def __init__(self, raw, nsamples, chunk=1 << 21, warm=1 << 19, overlap=8192, device=0, dist=None,
-                 interp_factor=5, two_pass=True, handoff=False, raw_first=0, seed_carrier=False, **cfg):
+                 interp_factor=5, two_pass=True, handoff=False, raw_first=0, seed_carrier=False, seed_nfft=1 << 17, **cfg):
         self.oqpsk_half = None
         if cfg.get("oqpsk"):
             # OQPSK: the join tells even from odd quarter turns by the half-symbol timing offset and the hand-off also
@@ -678,7 +688,7 @@ class ShardedDemod:
         if raw_first > plan.start(self.c0) or raw.numel() < need:
             raise ValueError("raw must hold samples [%d, %d) for chunks %d..%d" % (plan.start(self.c0), raw_first + need // 2, self.c0, self.c1 - 1))
         self.eng = GpuEngine(raw, plan, device=device, first_chunk=self.c0, nchunks=self.c1 - self.c0,
-                             raw_first=raw_first, seed_carrier=seed_carrier, **cfg)
+                             raw_first=raw_first, seed_carrier=seed_carrier, seed_nfft=seed_nfft, **cfg)
 
     def run(self, phase_ms=None):
         """phase_ms: optional dict that receives the wall time of each phase in ms (hand-off scheme)."""

@@ -127,6 +127,10 @@ def test_plan_geometry():
     assert p.nchunks == 5 and p.boundary(0) == 0 and p.boundary(1) == WARM + CHUNK
     assert p.boundary(p.nchunks - 1) < N <= WARM + p.nchunks * CHUNK
     assert p.padded >= N and p.start(3) == 3 * CHUNK
+    import dataclasses
+    for q in (p, dataclasses.replace(p, cut_shift=OVERLAP)):     # the vectorised form the joins use
+        assert q.cut_targets(1, q.nchunks).tolist() == [q.cut_target(c) for c in range(1, q.nchunks)]
+        assert q.cut_targets(3, 3).numel() == 0
     assert [sharded.split_chunks(5, 2, r) for r in (0, 1)] == [(0, 3), (3, 5)]
     # even split: no rank without chunks while nchunks >= world (5 over 4, 9 over 8), consecutive, complete
     assert [sharded.split_chunks(5, 4, r) for r in range(4)] == [(0, 2), (2, 3), (3, 4), (4, 5)]
@@ -699,6 +703,11 @@ def test_coarse_carrier_estimate():
         assert np.allclose(est.numpy(), cfos, atol=2.0), (oq, est.tolist())
         one = acquire.estimate_cfo(acquire.to_complex(rows[1], bps), 230000, symrate, bool(oq))
         assert abs(float(one) - cfos[1]) < 2.0
+    # a short transform (bins 56 Hz apart, 14 Hz in carrier terms for the x^4 line): the three-point parabola around the
+    # peak keeps the estimate within a few Hz -- 2e-4 rad/symbol, far inside what the loop pulls in while it locks
+    short = np.stack([synth.make_raw(4096, cfo_hz=f, seed=9 + i) for i, f in enumerate((-1234.0, 87.0, 700.0, 3001.0))])
+    est = acquire.estimate_cfo(acquire.to_complex(short, 16), 230000, 72000, False)
+    assert np.allclose(est.numpy(), (-1234.0, 87.0, 700.0, 3001.0), atol=4.0), est.tolist()
     pf = acquire.p_freq_for(700.0, 72000, False)
     assert abs(float(pf) * 72000 / (2 * np.pi) - 700.0) < 1e-3 and isinstance(pf, np.float32)
 
