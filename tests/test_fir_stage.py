@@ -42,6 +42,10 @@ def test_fir_stage_equals_filter_get(cfg, oracle_mod, lib):
                                        cfo_hz=100.0 * s) for s in range(3)])
         got = fir_stage(raw, cfg, 0)
         fma = fir_stage(raw, cfg, 1)
+        # bits 1-2 of mode force one or two output samples per thread: a tuning knob, never a different result
+        for ns in (1, 2):
+            assert np.array_equal(bits(fir_stage(raw, cfg, ns << 1)), bits(got)), (n, ns)
+            assert np.array_equal(bits(fir_stage(raw, cfg, (ns << 1) | 1)), bits(fma)), (n, ns)
         for s in range(3):
             want = oracle_mod.Oracle(**cfg).fir_all(raw[s])
             assert np.array_equal(bits(got[s]), bits(want)), (n, s)

@@ -431,6 +431,17 @@ def test_handle_stream_is_ordered_after_torch_stream(lib):
         d.process_device(raw, got)
         d.sync()
         cg = d.counts().copy()
+        # ... and the reverse: a torch stream that reads the symbols without a host synchronisation in between
+        lib_ = d.lib
+        side = torch.cuda.Stream()
+        d.reset()
+        d.process_device(raw, got)
+        assert lib_.lrpt_stream_release(d.h, side.cuda_stream) == 0
+        with torch.cuda.stream(side):
+            copy = got.clone()
+        side.synchronize()
+        d.sync()
+        assert torch.equal(copy, got)
     assert np.array_equal(cw, cg)
     m = torch.arange(24000, device="cuda")[None, :] < torch.as_tensor(cw.astype(np.int64), device="cuda")[:, None]
     m2 = m.repeat_interleave(2, dim=1)
