@@ -263,6 +263,9 @@ int  lrpt_sharded_process(const lrpt_params_t *p, const lrpt_shard_plan_t *plan,
  */
 int  lrpt_sharded_process_multi(const lrpt_params_t *p, const lrpt_shard_plan_t *plan, const void *raw_iq, size_t nsamples,
                                 int8_t *soft, size_t cap, size_t *nsym, lrpt_shard_report_t *rep, const int *devices, int ndev);
+/* The NCCL communicators of lrpt_sharded_process_multi are kept for the next call with the same device list (creating
+ * them costs more than demodulating a 2-GSample recording; one multi-GPU call runs at a time). This frees them. */
+void lrpt_sharded_release(void);
 
 /* ---- decoder front-end (csrc/frontend.cu) ----------------------------------------
  * The consumer of this path's output in the reference's pipeline (README.md:6-9,87-91: the `.s` soft-symbol file

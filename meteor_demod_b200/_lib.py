@@ -99,6 +99,7 @@ SYMBOLS = {
     "lrpt_unpin_host": (C.c_int, [C.c_void_p]),
     "lrpt_fir_stage_device": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p,
                                         C.c_size_t, C.c_int, C.c_void_p]),
+    "lrpt_sharded_release": (None, []),
     "lrpt_sharded_process_multi": (C.c_int, [C.POINTER(Params), C.POINTER(ShardPlan), C.c_void_p, C.c_size_t, C.c_void_p,
                                              C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(ShardReport), C.c_void_p, C.c_int]),
     "lrpt_describe": (C.c_int, [C.POINTER(Params), C.POINTER(State), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -50,6 +50,22 @@ struct DevBuf {
 	template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
+/* Small device arrays (per-boundary / per-row tables of the joins) come out of one allocation per rank: a cudaMalloc +
+ * cudaFree pair costs up to a millisecond next to multi-GB buffers, and the joins need some thirty of them. */
+struct Arena {
+	DevBuf buf;
+	size_t cap = 0, used = 0;
+	cudaError_t init(size_t bytes) { cap = bytes; used = 0; return buf.alloc(bytes); }
+	void reset() { used = 0; }
+	template <class T> T *take(size_t count)
+	{
+		const size_t at = (used + 255) & ~(size_t)255, need = count*sizeof(T);
+		if (!buf.p || at + need > cap) return nullptr;
+		used = at + need;
+		return reinterpret_cast<T *>(buf.as<char>() + at);
+	}
+};
+
 struct Handle {
 	lrpt_demod_t *h = nullptr;
 	~Handle() { if (h) lrpt_destroy(h); }
@@ -79,42 +95,41 @@ struct Phases {
 #define RC(x) do { const int rc_ = (x); if (rc_) return rc_; } while (0)
 
 /* boundaries between consecutive rows [r0, r0 + n): k, agreement and cut per boundary (host vectors) */
-int scan_rows(const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride, const int32_t *d_count,
+int scan_rows(Arena &ar, const int8_t *d_soft, size_t soft_stride, const uint32_t *d_q, size_t q_stride, const int32_t *d_count,
               const int64_t *d_base, int n, const std::vector<int64_t> &target, std::vector<int32_t> &k,
               std::vector<float> &agree, std::vector<int64_t> &cut, float oqpsk_half = 0.0f)
 {
 	const int nb = n - 1;
 	k.assign(nb > 0 ? nb : 0, 0); agree.assign(nb > 0 ? nb : 0, 0.0f); cut.assign(nb > 0 ? nb : 0, 0);
 	if (nb <= 0) return LRPT_OK;
-	DevBuf tgt, dcut, ia, ib, nav, dk, same;
-	CK(tgt.alloc(8*(size_t)nb)); CK(dcut.alloc(8*(size_t)nb)); CK(ia.alloc(4*(size_t)nb)); CK(ib.alloc(4*(size_t)nb));
-	CK(nav.alloc(4*(size_t)nb)); CK(dk.alloc(4*(size_t)nb)); CK(same.alloc(4*(size_t)nb));
-	CK(cudaMemcpy(tgt.p, target.data(), 8*(size_t)nb, cudaMemcpyHostToDevice));
-	RC(lrpt_shard_find_cuts_device(d_q, q_stride, d_count, d_base, n, tgt.as<int64_t>(), dcut.as<int64_t>(), ia.as<int32_t>(),
-	                               ib.as<int32_t>(), nav.as<int32_t>(), nullptr));
+	ar.reset();
+	int64_t *tgt = ar.take<int64_t>(nb), *dcut = ar.take<int64_t>(nb);
+	int32_t *ia = ar.take<int32_t>(nb), *ib = ar.take<int32_t>(nb), *nav = ar.take<int32_t>(nb), *dk = ar.take<int32_t>(nb),
+	        *same = ar.take<int32_t>(nb);
+	if (!tgt || !dcut || !ia || !ib || !nav || !dk || !same) return LRPT_ERR_NOMEM;
+	CK(cudaMemcpy(tgt, target.data(), 8*(size_t)nb, cudaMemcpyHostToDevice));
+	RC(lrpt_shard_find_cuts_device(d_q, q_stride, d_count, d_base, n, tgt, dcut, ia, ib, nav, nullptr));
 	std::vector<int32_t> navail(nb);
-	CK(cudaMemcpy(navail.data(), nav.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
-	CK(cudaMemcpy(cut.data(), dcut.p, 8*(size_t)nb, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(navail.data(), nav, 4*(size_t)nb, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(cut.data(), dcut, 8*(size_t)nb, cudaMemcpyDeviceToHost));
 	int npairs = INT_MAX;
 	for (int v : navail) npairs = v < npairs ? v : npairs;
 	if (oqpsk_half > 0.0f) {
 		/* one symbol of the earlier row in reserve (the odd pairing reads a.I of the NEXT symbol), and every boundary
 		 * needs a symbol of that row in front of its first pair (sharded.py::boundary_quadrants_oqpsk) */
 		std::vector<int32_t> via(nb);
-		CK(cudaMemcpy(via.data(), ia.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(via.data(), ia, 4*(size_t)nb, cudaMemcpyDeviceToHost));
 		npairs = npairs > 0 ? npairs - 1 : 0;
 		for (int v : via) if (v <= 0) npairs = 0;
 	}
 	if (npairs < 8) return LRPT_OK;                                 /* k = 0, agreement = 0: the caller reports it */
 	if (oqpsk_half > 0.0f)
-		RC(lrpt_shard_quadrants_oqpsk_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia.as<int32_t>(), ib.as<int32_t>(), npairs,
-		                                     oqpsk_half, dk.as<int32_t>(), same.as<int32_t>(), nullptr));
+		RC(lrpt_shard_quadrants_oqpsk_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia, ib, npairs, oqpsk_half, dk, same, nullptr));
 	else
-		RC(lrpt_shard_quadrants_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia.as<int32_t>(), ib.as<int32_t>(), npairs,
-		                               dk.as<int32_t>(), same.as<int32_t>(), nullptr));
+		RC(lrpt_shard_quadrants_device(d_soft, soft_stride, d_q, q_stride, d_base, n, ia, ib, npairs, dk, same, nullptr));
 	std::vector<int32_t> s(nb);
-	CK(cudaMemcpy(k.data(), dk.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
-	CK(cudaMemcpy(s.data(), same.p, 4*(size_t)nb, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(k.data(), dk, 4*(size_t)nb, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(s.data(), same, 4*(size_t)nb, cudaMemcpyDeviceToHost));
 	for (int b = 0; b < nb; b++) agree[b] = (float)s[b]/(float)npairs;
 	return LRPT_OK;
 }
@@ -143,6 +158,38 @@ struct Nccl {
 	}
 };
 constexpr int NCCL_CHAR = 0;                                    /* ncclInt8 / ncclChar */
+
+/* Communicators are kept between calls: ncclCommInitAll and the first exchange on a fresh communicator cost ~0.5 s,
+ * more than the whole demodulation of a 2-GSample recording. One multi-GPU call at a time uses them (the mutex is held
+ * for the whole call); a different device list replaces them; lrpt_sharded_release() frees them. */
+struct CommCache {
+	pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+	Nccl nccl;
+	bool loaded = false;
+	std::vector<int> devs;
+	std::vector<ncclComm_t> comms;
+	void drop()
+	{
+		for (ncclComm_t c : comms) if (c) nccl.CommDestroy(c);
+		comms.clear(); devs.clear();
+	}
+	/* 0 on success; the caller holds mu */
+	int get(const int *devices, int world)
+	{
+		if (!loaded) {
+			if (!nccl.load()) { fprintf(stderr, "lrpt_sharded_process_multi: libnccl.so.2 not found\n"); return LRPT_ERR_CUDA; }
+			loaded = true;
+		}
+		std::vector<int> want(devices, devices + world);
+		if (want == devs && (int)comms.size() == world) return LRPT_OK;
+		drop();
+		comms.assign(world, nullptr);
+		if (nccl.CommInitAll(comms.data(), world, devices)) { comms.clear(); return LRPT_ERR_CUDA; }
+		devs = want;
+		return LRPT_OK;
+	}
+};
+CommCache g_comms;
 
 /* What the rank threads share (host memory): integers only. */
 struct Shared {
@@ -231,6 +278,7 @@ struct Rank {
 		/* OQPSK: timing sub-steps in half a symbol; 0 = QPSK join */
 		const float oq_half = params.oqpsk ? (float)((double)params.samplerate*(double)params.interp_factor/(2.0*(double)params.symrate)) : 0.0f;
 		int rc = LRPT_OK;
+		const auto t_start = std::chrono::steady_clock::now();
 		Phases ph(first);
 		auto fail = [&](int code) { if (!rc) rc = code; sh->rc[rank] = rc; };
 #define TRY(x) do { if (!rc) { const int rc_ = (x); if (rc_) fail(rc_); } } while (0)
@@ -251,6 +299,8 @@ struct Rank {
 		const size_t cap_row = (symbol_capacity(W > n_row ? W : n_row, p) + 7)/8*8;
 		const size_t soft_stride = 2*cap_row, q_stride = 4*cap_row;
 		DevBuf d_raw, d_soft, d_q, d_nsym, d_cnt, d_base, d_states, d_pack, d_two_soft, d_two_q, d_two_cnt, d_two_base, d_st_io;
+		Arena ar;
+		TRYCU(ar.init(64*M + 65536));
 		TRYCU(d_raw.alloc(span*bytes)); TRYCU(d_soft.alloc(M*soft_stride)); TRYCU(d_q.alloc(M*q_stride)); TRYCU(d_nsym.alloc(4*M));
 		TRYCU(d_cnt.alloc(4*M)); TRYCU(d_base.alloc(8*M));
 		/* a boundary row on its way to the next rank: symbols, sub-step indices, then count (int32) and base (int64) */
@@ -306,7 +356,7 @@ struct Rank {
 			std::vector<int64_t> tgt(1, cut_target(c0, shift)), cut;
 			std::vector<int32_t> k;
 			std::vector<float> ag;
-			TRY(scan_rows(d_two_soft.as<int8_t>(), soft_stride, d_two_q.as<uint32_t>(), q_stride, d_two_cnt.as<int32_t>(),
+			TRY(scan_rows(ar, d_two_soft.as<int8_t>(), soft_stride, d_two_q.as<uint32_t>(), q_stride, d_two_cnt.as<int32_t>(),
 			              d_two_base.as<int64_t>(), 2, tgt, k, ag, cut, oq_half));
 			if (!rc) { k_prev = k[0]; agree_prev = ag[0]; cut_prev = cut[0]; }
 		};
@@ -328,7 +378,7 @@ struct Rank {
 		std::vector<int32_t> k;
 		std::vector<float> agree;
 		for (size_t c = 1; c < M; c++) target[c - 1] = cut_target(c0 + c, 0);
-		TRY(scan_rows(d_soft.as<int8_t>(), soft_stride, d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), (int)M,
+		TRY(scan_rows(ar, d_soft.as<int8_t>(), soft_stride, d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), (int)M,
 		              target, k, agree, cut, oq_half));
 		if (rc) { k.assign(M > 1 ? M - 1 : 0, 0); agree.assign(k.size(), 0.0f); }
 		int32_t k_prev = 0; float agree_prev = 1.0f; int64_t cut_prev = -1;
@@ -351,14 +401,15 @@ struct Rank {
 		}
 		if (first && !rc) {
 			/* chunk 0's pass-B symbols continue the head, up to the end of the stream */
-			DevBuf lo, hi, stt, ln;
 			const int64_t l = -1, hh = (int64_t)nsamples*L - 1;
 			int32_t s_0 = 0, n_0 = 0;
-			TRYCU(lo.alloc(8)); TRYCU(hi.alloc(8)); TRYCU(stt.alloc(4)); TRYCU(ln.alloc(4));
-			TRYCU(cudaMemcpy(lo.p, &l, 8, cudaMemcpyHostToDevice)); TRYCU(cudaMemcpy(hi.p, &hh, 8, cudaMemcpyHostToDevice));
-			TRY(lrpt_shard_ranges_device(d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), 1, lo.as<int64_t>(),
-			                             hi.as<int64_t>(), stt.as<int32_t>(), ln.as<int32_t>(), nullptr));
-			TRYCU(cudaMemcpy(&s_0, stt.p, 4, cudaMemcpyDeviceToHost)); TRYCU(cudaMemcpy(&n_0, ln.p, 4, cudaMemcpyDeviceToHost));
+			ar.reset();
+			int64_t *lo = ar.take<int64_t>(1), *hi = ar.take<int64_t>(1);
+			int32_t *stt = ar.take<int32_t>(1), *ln = ar.take<int32_t>(1);
+			if (!lo || !hi || !stt || !ln) fail(LRPT_ERR_NOMEM);
+			TRYCU(cudaMemcpy(lo, &l, 8, cudaMemcpyHostToDevice)); TRYCU(cudaMemcpy(hi, &hh, 8, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_ranges_device(d_q.as<uint32_t>(), q_stride, d_cnt.as<int32_t>(), d_base.as<int64_t>(), 1, lo, hi, stt, ln, nullptr));
+			TRYCU(cudaMemcpy(&s_0, stt, 4, cudaMemcpyDeviceToHost)); TRYCU(cudaMemcpy(&n_0, ln, 4, cudaMemcpyDeviceToHost));
 			if (!rc) {
 				const size_t at = head.size();
 				head.resize(at + 2*(size_t)n_0);
@@ -431,7 +482,7 @@ struct Rank {
 		std::vector<int32_t> k2;
 		std::vector<float> agree2;
 		for (int b = 0; b + 1 < n; b++) target2[b] = cut_target(c0 + skip + (size_t)b + 1, V);
-		TRY(scan_rows(soft1, soft_stride, q1, q_stride, cnt1, base1, n, target2, k2, agree2, cut2, oq_half));
+		TRY(scan_rows(ar, soft1, soft_stride, q1, q_stride, cnt1, base1, n, target2, k2, agree2, cut2, oq_half));
 		if (rc) { k2.assign(n > 1 ? n - 1 : 0, 0); agree2.assign(k2.size(), 0.0f); cut2.assign(k2.size(), 0); }
 		int32_t k_prev2 = 0; float agree_prev2 = 1.0f; int64_t cut_prev2 = -1;
 		boundary_with_prev(V, k_prev2, agree_prev2, cut_prev2);
@@ -456,13 +507,15 @@ struct Rank {
 			const int64_t two_b[2] = { base[r], base[r] };
 			TRYCU(cudaMemcpy(d_two_cnt.p, two_c, 8, cudaMemcpyHostToDevice));
 			TRYCU(cudaMemcpy(d_two_base.p, two_b, 16, cudaMemcpyHostToDevice));
-			DevBuf tgt, dcut, ia, ib, nav;
 			const int64_t t = cut_target(c1, V);
-			TRYCU(tgt.alloc(8)); TRYCU(dcut.alloc(8)); TRYCU(ia.alloc(4)); TRYCU(ib.alloc(4)); TRYCU(nav.alloc(4));
-			TRYCU(cudaMemcpy(tgt.p, &t, 8, cudaMemcpyHostToDevice));
+			ar.reset();
+			int64_t *tgt = ar.take<int64_t>(1), *dcut = ar.take<int64_t>(1);
+			int32_t *ia = ar.take<int32_t>(1), *ib = ar.take<int32_t>(1), *nav = ar.take<int32_t>(1);
+			if (!tgt || !dcut || !ia || !ib || !nav) fail(LRPT_ERR_NOMEM);
+			TRYCU(cudaMemcpy(tgt, &t, 8, cudaMemcpyHostToDevice));
 			TRY(lrpt_shard_find_cuts_device(d_two_q.as<uint32_t>(), q_stride, d_two_cnt.as<int32_t>(), d_two_base.as<int64_t>(), 2,
-			                                tgt.as<int64_t>(), dcut.as<int64_t>(), ia.as<int32_t>(), ib.as<int32_t>(), nav.as<int32_t>(), nullptr));
-			TRYCU(cudaMemcpy(&hi_last, dcut.p, 8, cudaMemcpyDeviceToHost));
+			                                tgt, dcut, ia, ib, nav, nullptr));
+			TRYCU(cudaMemcpy(&hi_last, dcut, 8, cudaMemcpyDeviceToHost));
 		}
 		sync();                                                     /* second round of quarter-turn sums */
 		std::vector<int32_t> turns(n > 0 ? n : 0, 0);
@@ -478,25 +531,25 @@ struct Rank {
 			}
 			hi[n - 1] = hi_last;
 		}
-		DevBuf dlo, dhi, dst, dln, doff, dturn, dout;
+		DevBuf dout;
 		std::vector<int32_t> len(n > 0 ? n : 0, 0), start(n > 0 ? n : 0, 0);
 		std::vector<int64_t> off(n > 0 ? n : 0, 0);
 		size_t total = 0, longest = 0;
 		if (n > 0) {
-			TRYCU(dlo.alloc(8*(size_t)n)); TRYCU(dhi.alloc(8*(size_t)n)); TRYCU(dst.alloc(4*(size_t)n)); TRYCU(dln.alloc(4*(size_t)n));
-			TRYCU(doff.alloc(8*(size_t)n)); TRYCU(dturn.alloc(4*(size_t)n));
-			TRYCU(cudaMemcpy(dlo.p, lo.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
-			TRYCU(cudaMemcpy(dhi.p, hi.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
-			TRY(lrpt_shard_ranges_device(q1, q_stride, cnt1, base1, n, dlo.as<int64_t>(), dhi.as<int64_t>(), dst.as<int32_t>(),
-			                             dln.as<int32_t>(), nullptr));
-			TRYCU(cudaMemcpy(len.data(), dln.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
-			TRYCU(cudaMemcpy(start.data(), dst.p, 4*(size_t)n, cudaMemcpyDeviceToHost));
+			ar.reset();
+			int64_t *dlo = ar.take<int64_t>(n), *dhi = ar.take<int64_t>(n), *doff = ar.take<int64_t>(n);
+			int32_t *dst = ar.take<int32_t>(n), *dln = ar.take<int32_t>(n), *dturn = ar.take<int32_t>(n);
+			if (!dlo || !dhi || !doff || !dst || !dln || !dturn) fail(LRPT_ERR_NOMEM);
+			TRYCU(cudaMemcpy(dlo, lo.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
+			TRYCU(cudaMemcpy(dhi, hi.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_ranges_device(q1, q_stride, cnt1, base1, n, dlo, dhi, dst, dln, nullptr));
+			TRYCU(cudaMemcpy(len.data(), dln, 4*(size_t)n, cudaMemcpyDeviceToHost));
+			TRYCU(cudaMemcpy(start.data(), dst, 4*(size_t)n, cudaMemcpyDeviceToHost));
 			if (!rc) for (int b = 0; b < n; b++) { off[b] = (int64_t)total; total += (size_t)len[b]; longest = (size_t)len[b] > longest ? (size_t)len[b] : longest; }
 			TRYCU(dout.alloc(2*total));
-			TRYCU(cudaMemcpy(doff.p, off.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
-			TRYCU(cudaMemcpy(dturn.p, turns.data(), 4*(size_t)n, cudaMemcpyHostToDevice));
-			TRY(lrpt_shard_gather_device(soft1, soft_stride, n, longest, dst.as<int32_t>(), dln.as<int32_t>(), doff.as<int64_t>(),
-			                             dturn.as<int32_t>(), dout.as<int8_t>(), nullptr));
+			TRYCU(cudaMemcpy(doff, off.data(), 8*(size_t)n, cudaMemcpyHostToDevice));
+			TRYCU(cudaMemcpy(dturn, turns.data(), 4*(size_t)n, cudaMemcpyHostToDevice));
+			TRY(lrpt_shard_gather_device(soft1, soft_stride, n, longest, dst, dln, doff, dturn, dout.as<int8_t>(), nullptr));
 		}
 		const size_t out_n = head.size()/2;                         /* rank 0: chunk 0's own symbols come first */
 		sh->nsym_rank[rank] = rc ? 0 : (long long)(out_n + total);
@@ -535,6 +588,9 @@ struct Rank {
 		ph.mark("D2H of the symbols");
 		if (st) cudaStreamDestroy(st);
 		sh->rc[rank] = rc;
+		if (getenv("LRPT_SHARD_TIMING"))
+			fprintf(stderr, "lrpt_sharded_process: rank %d of %d, rows %zu, %.2f ms from thread start to results\n", rank, world, M,
+			        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
 		return rc;
 #undef TRY
 #undef TRYCU
@@ -594,12 +650,13 @@ extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrp
 	sh.rc.assign(world, 0); sh.ksum.assign(world, 0); sh.ksum2.assign(world, 0); sh.aligned.assign(world, 1); sh.launches.assign(world, 0);
 	sh.agree_scan.assign(world, 1.0f); sh.agree_final.assign(world, 1.0f);
 	sh.nsym_rank.assign(world, 0); sh.first_lock_rank.assign(world, -1);
-	Nccl nccl;
+	const auto t_call = std::chrono::steady_clock::now();
 	if (world > 1) {
-		if (!nccl.load()) { fprintf(stderr, "lrpt_sharded_process_multi: libnccl.so.2 not found\n"); return LRPT_ERR_CUDA; }
-		sh.nccl = &nccl;
-		sh.comms.assign(world, nullptr);
-		if (nccl.CommInitAll(sh.comms.data(), world, devices)) return LRPT_ERR_CUDA;
+		pthread_mutex_lock(&g_comms.mu);
+		const int rc = g_comms.get(devices, world);
+		if (rc) { pthread_mutex_unlock(&g_comms.mu); return rc; }
+		sh.nccl = &g_comms.nccl;
+		sh.comms = g_comms.comms;
 	}
 	pthread_barrier_init(&sh.bar, nullptr, (unsigned)world);
 	std::vector<Rank> ranks(world);
@@ -618,7 +675,13 @@ extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrp
 	if (started == world) ranks[0].run();
 	for (int i = 1; i < started; i++) pthread_join(tids[i], nullptr);
 	pthread_barrier_destroy(&sh.bar);
-	if (world > 1) for (int i = 0; i < world; i++) if (sh.comms[i]) nccl.CommDestroy(sh.comms[i]);
+	if (world > 1) {
+		if (sh.failed() || started != world) g_comms.drop();         /* a failed exchange may have left them unusable */
+		pthread_mutex_unlock(&g_comms.mu);
+	}
+	if (getenv("LRPT_SHARD_TIMING"))
+		fprintf(stderr, "lrpt_sharded_process: %d device(s), %.2f ms in the call so far (threads joined, buffers freed)\n", world,
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
 	if (started != world) return LRPT_ERR_NOMEM;
 	for (int i = 0; i < world; i++) if (sh.rc[i]) return sh.rc[i];
 
@@ -636,6 +699,13 @@ extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrp
 	r.launches /= world;                                            /* launches per GPU: the three passes */
 	if (rep) *rep = r;
 	return LRPT_OK;
+}
+
+extern "C" void lrpt_sharded_release(void)
+{
+	pthread_mutex_lock(&g_comms.mu);
+	g_comms.drop();
+	pthread_mutex_unlock(&g_comms.mu);
 }
 
 extern "C" int lrpt_sharded_process(const lrpt_params_t *params, const lrpt_shard_plan_t *plan, const void *raw_iq,
