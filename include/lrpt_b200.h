@@ -322,6 +322,17 @@ int   lrpt_unpin_host(void *p);
 int  lrpt_fir_stage_device(const lrpt_params_t *p, const void *d_raw, size_t raw_stride, int nrows, size_t nsamples,
                            float *d_out, size_t out_stride, int mode, void *cuda_stream);
 
+/* ---- coarse carrier estimate (csrc/acquire.cu) ------------------------------------
+ * Not in the reference: it finds the carrier by sweeping its Costas NCO at 1e-6 rad/symbol^2 until the lock detector
+ * fires (pll.c:117-128). Time-sharded chunks skip that wait: every chunk but the first starts with p_freq =
+ * 2*pi*f_c/(symrate * (oqpsk ? 2 : 1)) (main.c:250 read backwards) for the f_c this returns.
+ * d_cfo_hz[row] = carrier offset in Hz of the first nfft samples (a power of two, 256..16384) of each of `nrows` rows,
+ * searched within +-fmax_hz: DC removed, x^4 (QPSK: line at 4 f_c) or x^2 (OQPSK: lines at 2 f_c -+ symrate), Hann
+ * window, FFT, strongest candidate, three-point parabola. Strides in bytes; rows aligned to one I/Q pair.
+ * Asynchronous on cuda_stream. */
+int  lrpt_carrier_estimate_device(const lrpt_params_t *p, const void *d_raw, size_t raw_stride, int nrows, int nfft,
+                                  double fmax_hz, double *d_cfo_hz, void *cuda_stream);
+
 /* ---- introspection -------------------------------------------------------------- */
 /*
  * Host-only (needs no CUDA device): what lrpt_create derives from `p`, exactly as

@@ -97,6 +97,8 @@ SYMBOLS = {
     "lrpt_free_host": (None, [C.c_void_p]),
     "lrpt_pin_host": (C.c_int, [C.c_void_p, C.c_size_t]),
     "lrpt_unpin_host": (C.c_int, [C.c_void_p]),
+    "lrpt_carrier_estimate_device": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_double,
+                                               C.c_void_p, C.c_void_p]),
     "lrpt_fir_stage_device": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p,
                                         C.c_size_t, C.c_int, C.c_void_p]),
     "lrpt_sharded_release": (None, []),

@@ -63,6 +63,24 @@ def estimate_cfo(x, fs, symrate, oqpsk, fmax=4000.0):
     return best[0] if one else best
 
 
+def estimate_cfo_device(rows, params, nfft, fmax=4000.0):
+    """The same estimate by the library's own kernel (csrc/acquire.cu, lrpt_carrier_estimate_device): rows is a CUDA
+    tensor [M, >= 2*nfft] of the raw dtype (any row stride), params the lrpt_params_t of the stream; nfft a power of two
+    in 256..16384. Returns float64 [M] on the device, asynchronous on torch's current stream."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    out = torch.empty(rows.shape[0], dtype=torch.float64, device=rows.device)
+    with torch.cuda.device(rows.device):
+        rc = lib.lrpt_carrier_estimate_device(C.byref(params), rows.data_ptr(), rows.stride(0) * rows.element_size(), rows.shape[0],
+                                              int(nfft), float(fmax), out.data_ptr(),
+                                              C.c_void_p(torch.cuda.current_stream(rows.device).cuda_stream))
+    if rc:
+        raise _lib.LrptError(rc, "lrpt_carrier_estimate_device")
+    return out
+
+
 def p_freq_for(cfo_hz, symrate, oqpsk):
     """Costas NCO step (radians per loop update, float32) that tracks a carrier offset: the inverse of the status
     line's conversion freq_hz = pll_freq*symrate/(2*pi)*(oqpsk ? 2 : 1) (main.c:250, pll.c:38)."""

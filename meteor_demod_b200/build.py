@@ -14,7 +14,7 @@ SO = os.path.join(HERE, "liblrpt_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CC = os.environ.get("CC", "gcc")
-CU_SOURCES = ["lrpt_api.cu", "demod_simple.cu", "demod_ws.cu", "demod_spec.cu", "demod_lane.cu", "shard_stitch.cu", "shard_run.cu", "fir_stage.cu", "frontend.cu"]
+CU_SOURCES = ["lrpt_api.cu", "demod_simple.cu", "demod_ws.cu", "demod_spec.cu", "demod_lane.cu", "shard_stitch.cu", "shard_run.cu", "fir_stage.cu", "frontend.cu", "acquire.cu"]
 C_SOURCES = ["lrpt_params.c"]
 HEADERS = ["demod_core.cuh", "ws_common.cuh", "kernels.h", "lrpt_internal.h", os.path.join(INC, "lrpt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

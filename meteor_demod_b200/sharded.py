@@ -42,6 +42,9 @@ import numpy as np
 import torch
 
 
+NATIVE_ESTIMATOR = True     # seeded warm-ups: the library's kernel (csrc/acquire.cu) instead of the torch.fft form of acquire.py
+
+
 def _on_device(soft, q, base):
     """Rows as the GPU engine leaves them: int32 row-local sub-step indices + a base per row, on the
     device. Those are joined by the library's stitch kernels (csrc/shard_stitch.cu); anything else (CPU
@@ -492,13 +495,21 @@ class GpuEngine:
             group = max(64, (1 << 25) // nfft)
         rows = self.export_rows()
         off = State.p_freq.offset
-        for r0 in range(0, self.M, group):
-            r1 = min(self.M, r0 + group)
-            x = acquire.to_complex(self._view(0, nfft)[r0:r1], par.bps)
-            f = acquire.estimate_cfo(x, par.samplerate, par.symrate, bool(par.oqpsk))
+        pow2 = nfft >= 256 and nfft <= 16384 and (nfft & (nfft - 1)) == 0
+        if self.raw.is_cuda and pow2 and NATIVE_ESTIMATOR:
+            # one launch of the library's own estimator over all rows (csrc/acquire.cu)
+            f = acquire.estimate_cfo_device(self._view(0, nfft), par, nfft)
             pf = acquire.p_freq_for(f, par.symrate, bool(par.oqpsk))
-            first = 1 if self.first + r0 == 0 else 0
-            rows[r0 + first: r1, off: off + 4] = pf[first:].contiguous().view(-1, 1).view(torch.uint8)
+            first = 1 if self.first == 0 else 0
+            rows[first:, off: off + 4] = pf[first:].contiguous().view(-1, 1).view(torch.uint8)
+        else:
+            for r0 in range(0, self.M, group):
+                r1 = min(self.M, r0 + group)
+                x = acquire.to_complex(self._view(0, nfft)[r0:r1], par.bps)
+                f = acquire.estimate_cfo(x, par.samplerate, par.symrate, bool(par.oqpsk))
+                pf = acquire.p_freq_for(f, par.symrate, bool(par.oqpsk))
+                first = 1 if self.first + r0 == 0 else 0
+                rows[r0 + first: r1, off: off + 4] = pf[first:].contiguous().view(-1, 1).view(torch.uint8)
         self.import_rows(rows)
 
     # -- hand-off scheme (run_handoff) -----------------------------------------------------------------

@@ -539,6 +539,41 @@ def test_gpu_seeded_warm_up(lib, oracle_mod):
     n01 = int(plan.boundary(2) * 80000 / 230000) - 16
     assert np.array_equal(a[:n01], seq[:n01])
     assert rep["frac_gt1"] < 0.01, rep
+    # the same with a short transform, which goes through the library's own estimator kernel (csrc/acquire.cu)
+    short = sharded.demod_sharded(dev, n, seed_carrier=True, seed_nfft=8192, **kw)
+    b = short["soft"].cpu().numpy()
+    rep = tier_s_report(b, seq)
+    assert rep["n_stitched"] == rep["n_seq"] and float(short["agreement"].min()) > 0.99 and rep["frac_gt1"] < 0.01, rep
+    assert np.array_equal(b[:n01], seq[:n01])
+
+
+@pytest.mark.gpu
+def test_native_carrier_estimate_equals_torch_form(lib):
+    """lrpt_carrier_estimate_device against acquire.estimate_cfo (torch.fft) on the same rows: both sample formats'
+    conversions, QPSK and OQPSK lines, several transform lengths, rows inside a wider strided buffer."""
+    import ctypes as C
+    from meteor_demod_b200 import _lib, acquire, synth
+    from meteor_demod_b200.demod import make_params
+    for oq, symrate, bps, nfft in ((0, 72000, 16, 4096), (0, 72000, 16, 16384), (1, 80000, 8, 8192), (1, 72000, 32, 4096),
+                                   (0, 72000, 8, 256)):
+        cfos = (-3300.0, -900.0, 60.0, 700.0, 2500.0)
+        rows = np.stack([synth.make_raw(nfft + 40, symrate=symrate, oqpsk=bool(oq), bps=bps, cfo_hz=f, seed=3 + i)
+                         for i, f in enumerate(cfos)])
+        t = torch.from_numpy(rows).cuda()
+        par = make_params(symrate=symrate, oqpsk=oq, bps=bps)
+        want = acquire.estimate_cfo(acquire.to_complex(t[:, : 2 * nfft], bps), 230000, symrate, bool(oq))
+        got = acquire.estimate_cfo_device(t, par, nfft)                       # row stride wider than the transform
+        torch.cuda.synchronize()
+        tol = 0.05 if nfft >= 4096 else 0.5
+        assert np.allclose(got.cpu().numpy(), want.cpu().numpy(), atol=tol), (oq, bps, nfft, got.tolist(), want.tolist())
+        if nfft >= 4096:
+            assert np.allclose(got.cpu().numpy(), cfos, atol=4.0)
+    L = _lib.load()
+    out = torch.zeros(5, dtype=torch.float64, device="cuda")
+    args = (t.data_ptr(), t.stride(0) * t.element_size(), 5)
+    assert L.lrpt_carrier_estimate_device(C.byref(par), *args, 3000, 4000.0, out.data_ptr(), None) == _lib.LRPT_ERR_ARG   # not a power of two
+    assert L.lrpt_carrier_estimate_device(C.byref(par), *args, 128, 4000.0, out.data_ptr(), None) == _lib.LRPT_ERR_ARG
+    assert L.lrpt_carrier_estimate_device(C.byref(par), *args, 256, 1.0e6, out.data_ptr(), None) == _lib.LRPT_ERR_ARG      # candidates would wrap
 
 
 def test_long_stream_windows_are_consistent():
