@@ -46,7 +46,7 @@
 #define VERSION "1.0-b200"
 #endif
 
-enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD, OPT_TUI, OPT_GPUS };
+enum { OPT_STDOUT = 0x100, OPT_DEVICE, OPT_REFTAIL, OPT_SHARD, OPT_TUI, OPT_GPUS, OPT_SEED };
 
 static struct option longopts[] = {
 	{ "batch",        0, NULL, 'B' }, { "pll-bw",       1, NULL, 'b' },
@@ -59,6 +59,7 @@ static struct option longopts[] = {
 	{ "version",      0, NULL, 'v' }, { "device",       1, NULL, OPT_DEVICE },
 	{ "ref-compatible-tail", 0, NULL, OPT_REFTAIL }, { "shard", 1, NULL, OPT_SHARD },
 	{ "tui",          0, NULL, OPT_TUI },          { "gpus",         1, NULL, OPT_GPUS },
+	{ "seed",         1, NULL, OPT_SEED },
 	{ NULL, 0, NULL, 0 }
 };
 
@@ -80,10 +81,13 @@ usage(const char *pname)
 	        "       --ref-compatible-tail  Final flush writes the reference's byte count (main.c:321)\n"
 	        "       --tui               Full-screen status with constellation plot (default on a terminal without -B)\n"
 	        "       --shard <samples>   Offline speed-up for ONE long recording: cut it into chunks of <samples>\n"
-	        "                           (e.g. 256k) demodulated side by side on the GPU and joined; QPSK only;\n"
+	        "                           (e.g. 256k) demodulated side by side on the GPU and joined;\n"
 	        "                           statistical parity (the first two chunks are exact), see DESIGN.md\n"
 	        "       --gpus <n>          With --shard: spread the chunks over CUDA devices <device> .. <device>+n-1 (state and\n"
 	        "                           overlap symbols of the boundary chunks travel over NCCL); same bytes as one GPU\n"
+	        "       --seed <n>          With --shard: chunks after the first start at a coarse carrier estimate over their\n"
+	        "                           first <n> samples (a power of two, 256..16384) and warm up over 32768 samples\n"
+	        "                           instead of repeating the acquisition sweep over 150000\n"
 	        "   Several input files are demodulated together as one batch; output goes to <file_in>.s each\n"
 	        "\n"
 	        "   -h, --help              Print this help screen\n"
@@ -483,7 +487,7 @@ run_batch(int nfiles, char **names, lrpt_params_t p, int samplerate_opt, int bps
 /* --shard: the whole recording (whole 32 KiB blocks of it, wavfile.c:55) in memory, one lrpt_sharded_process
  * call, then the reference's egress rules (main.c:305-323) on the joined symbols. */
 static int
-run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float symrate, int quiet, int ref_tail, int gpus)
+run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float symrate, int quiet, int ref_tail, int gpus, int seed)
 {
 	size_t have = 0, room = (size_t)64 << 20;
 	int pinned = 0, pin_soft = 0;
@@ -525,7 +529,7 @@ run_sharded(FILE *in, FILE *out, const lrpt_params_t *p, size_t chunk, float sym
 	const size_t cap = (size_t)((double)nsamples*p->symrate/p->samplerate*1.02) + 64;
 	int8_t *soft = host_alloc(2*cap, &pin_soft);
 	if (!soft) { fprintf(stderr, "out of memory\n"); return 1; }
-	lrpt_shard_plan_t plan = { (chunk + 7)/8*8, 150000, 8192 };
+	lrpt_shard_plan_t plan = { (chunk + 7)/8*8, seed ? 32768 : 150000, 8192, (uint64_t)(seed > 0 ? seed : 0) };
 	lrpt_shard_report_t rep;
 	size_t nsym = 0;
 	int rc, devs[64], g;
@@ -554,7 +558,7 @@ main(int argc, char *argv[])
 {
 	float pll_bw = 1, symrate = 72000.0f, freq_max_delta = -1;
 	int rrc_order = 32, interp_factor = 5, quiet = 0, oqpsk = 0, batch = 0;
-	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0, tui = -1, gpus = 1;
+	int update_interval = -1, bps = 0, samplerate = -1, stdout_mode = 0, device = 0, ref_tail = 0, tui = -1, gpus = 1, seed = 0;
 	size_t shard = 0;
 	char *output_fname = NULL;
 	FILE *in, *out;
@@ -567,6 +571,7 @@ main(int argc, char *argv[])
 			case OPT_REFTAIL: ref_tail = 1; break;
 			case OPT_TUI: tui = 1; break;
 			case OPT_GPUS: gpus = atoi(optarg); break;
+			case OPT_SEED: seed = atoi(optarg); break;
 			case OPT_SHARD: shard = (size_t)human_to_float(optarg); break;
 			case 'b': pll_bw = human_to_float(optarg); break;
 			case 'B': batch = 1; break;
@@ -625,7 +630,7 @@ main(int argc, char *argv[])
 	p.device = device; p.nstreams = 1; p.kernel = LRPT_KERNEL_AUTO;
 	if (shard) {
 		if (!quiet) printf("Input: %s, output: %s\n", argv[optind], output_fname);
-		int src = run_sharded(in, out, &p, shard, symrate, quiet, ref_tail, gpus);
+		int src = run_sharded(in, out, &p, shard, symrate, quiet, ref_tail, gpus, seed);
 		if (out != stdout) fclose(out);
 		if (in != stdin) fclose(in);
 		return src;

@@ -240,7 +240,13 @@ int  lrpt_shard_gather_device(const int8_t *d_soft, size_t soft_stride, int nrow
  * soft: 2 int8 per symbol, ALL symbols in stream order (the host applies the 512-symbol lock gating with
  * rep->first_lock_symbol, which is chunk 0's: -1 if the loop had not locked by the end of chunk 0).
  */
-typedef struct lrpt_shard_plan { uint64_t chunk, warm, overlap; } lrpt_shard_plan_t;
+typedef struct lrpt_shard_plan {
+	uint64_t chunk, warm, overlap;
+	uint64_t seed_nfft;            /* 0: every chunk acquires the carrier as the reference does (pll.c:117-128; needs
+	                                * ~150 k samples of warm-up at 700 Hz). A power of two in 256..16384: chunks after the
+	                                * first start with their Costas NCO at lrpt_carrier_estimate_device's estimate over
+	                                * their first seed_nfft samples (32 Ki samples of warm-up are then enough)          */
+} lrpt_shard_plan_t;
 typedef struct lrpt_shard_report {
 	int32_t nchunks, launches;
 	float   min_agreement_scan;    /* worst boundary of the quadrant scan: share of overlap symbols agreeing  */

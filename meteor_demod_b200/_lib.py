@@ -38,7 +38,7 @@ class Status(C.Structure):
 
 
 class ShardPlan(C.Structure):
-    _fields_ = [("chunk", C.c_uint64), ("warm", C.c_uint64), ("overlap", C.c_uint64)]
+    _fields_ = [("chunk", C.c_uint64), ("warm", C.c_uint64), ("overlap", C.c_uint64), ("seed_nfft", C.c_uint64)]
 
 
 class ShardReport(C.Structure):

@@ -361,6 +361,32 @@ struct Rank {
 			if (!rc) { k_prev = k[0]; agree_prev = ag[0]; cut_prev = cut[0]; }
 		};
 
+		/* ---- optional: chunks after the stream's first start with their Costas NCO at a coarse carrier estimate instead
+		 * of sweeping to the carrier (sharded.py::GpuEngine::seed_carrier: p_freq, everything else power-on) ---- */
+		if (job.plan->seed_nfft && h && !rc) {
+			const int nfft = (int)job.plan->seed_nfft;
+			const size_t total = lrpt_states_size(h);
+			DevBuf d_cfo, d_pow;
+			std::vector<double> cfo(M, 0.0);
+			std::vector<char> st0(total);
+			TRYCU(d_cfo.alloc(8*M)); TRYCU(d_pow.alloc(total));
+			TRY(lrpt_carrier_estimate_device(&p, raw0, C*bytes, (int)M, nfft, 4000.0, d_cfo.as<double>(), nullptr));
+			TRYCU(cudaMemcpy(cfo.data(), d_cfo.p, 8*M, cudaMemcpyDeviceToHost));
+			TRY(lrpt_export_states_device(h, d_pow.p, total, nullptr));
+			TRY(lrpt_sync(h, nullptr));
+			TRYCU(cudaMemcpy(st0.data(), d_pow.p, total, cudaMemcpyDeviceToHost));
+			if (!rc) {
+				lrpt_state_t *s0 = reinterpret_cast<lrpt_state_t *>(st0.data());
+				const double per = (double)((long long)params.symrate*(params.oqpsk ? 2 : 1));
+				for (size_t c = first ? 1 : 0; c < M; c++)
+					s0[c].p_freq = (float)(2.0*3.14159265358979323846*cfo[c]/per);   /* acquire.py::p_freq_for; main.c:250 backwards */
+				TRYCU(cudaMemcpy(d_pow.p, st0.data(), total, cudaMemcpyHostToDevice));
+				TRYCU(cudaDeviceSynchronize());
+				TRY(lrpt_import_states_device(h, d_pow.p, total, 1, nullptr));
+				TRY(lrpt_sync(h, nullptr));
+			}
+			ph.mark("carrier estimates");
+		}
 		/* ---- pass A: warm-up; chunk 0's warm-up symbols open the output (they are the sequential run's) ---- */
 		std::vector<int8_t> head;                                   /* rank 0: chunk 0's own symbols (passes A and B) */
 		if (W) {
@@ -618,6 +644,10 @@ extern "C" int lrpt_sharded_process_multi(const lrpt_params_t *params, const lrp
 	const size_t C = plan->chunk, W = plan->warm, V = plan->overlap;
 	if (!C || !V || (C & 7) || (W & 7) || (V & 7)) return LRPT_ERR_ARG;             /* 16-byte aligned rows for every sample format */
 	if (params->bps != 8 && params->bps != 16 && params->bps != 32) return LRPT_ERR_ARG;
+	if (plan->seed_nfft) {
+		const uint64_t f = plan->seed_nfft;
+		if (f < 256 || f > 16384 || (f & (f - 1)) || f > W + C) return LRPT_ERR_ARG;
+	}
 	const size_t M = nsamples > W ? (nsamples - W + C - 1)/C : 1;
 	if (M > (size_t)INT_MAX/2) return LRPT_ERR_ARG;
 	/* the rows' sub-step indices (sample*interp + sub-step, uint32 side output) must not wrap: the joins

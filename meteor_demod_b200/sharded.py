@@ -748,14 +748,16 @@ def demod_sharded(raw, nsamples, **kw):
         sd.close()
 
 
-def process_host(raw, chunk=1 << 18, warm=150000, overlap=8192, out=None, devices=None, **cfg):
+def process_host(raw, chunk=1 << 18, warm=150000, overlap=8192, out=None, devices=None, seed_nfft=0, **cfg):
     """ONE recording in host memory, time-sharded on one GPU by a single C call (lrpt_sharded_process,
     csrc/shard_run.cu -- the hand-off scheme above without Python in the loop; what host/lrpt_demod --shard
     uses). raw: numpy array of interleaved I,Q in the configured sample format. cfg: make_params' keywords
     (symrate, bps, rrc_order, interp_factor, ...). out: optional int8 array [cap, 2] to receive the symbols
     (page-locked memory makes the final copy 15x faster than a fresh pageable array). devices: list of CUDA
     ordinals -> lrpt_sharded_process_multi (one host thread per GPU, boundary state and overlap symbols over NCCL;
-    byte-identical to the one-GPU call). Returns (soft [n,2] int8 -- a view of `out` when given --, report dict)."""
+    byte-identical to the one-GPU call). seed_nfft: 0, or the transform length of the coarse carrier estimate chunks
+    after the first start from (lrpt_shard_plan_t.seed_nfft). Returns (soft [n,2] int8 -- a view of `out` when given --,
+    report dict)."""
     from ._lib import LrptError, ShardPlan, ShardReport, load
     from .demod import make_params, symbol_capacity
     p = make_params(**cfg)
@@ -769,7 +771,7 @@ def process_host(raw, chunk=1 << 18, warm=150000, overlap=8192, out=None, device
         if soft.dtype != np.int8 or not soft.flags["C_CONTIGUOUS"] or soft.ndim != 2 or soft.shape[1] != 2:
             raise ValueError("out must be a C-contiguous int8 array [cap, 2]")
         cap = soft.shape[0]
-    nsym, rep, plan = C.c_size_t(0), ShardReport(), ShardPlan(chunk, warm, overlap)
+    nsym, rep, plan = C.c_size_t(0), ShardReport(), ShardPlan(chunk, warm, overlap, seed_nfft)
     if devices:
         devs = (C.c_int * len(devices))(*devices)
         rc = load().lrpt_sharded_process_multi(C.byref(p), C.byref(plan), a.ctypes.data, n, soft.ctypes.data, cap,

@@ -154,6 +154,14 @@ def test_shard_flag_one_long_recording(host, oracle_mod, tmp_path):
     assert np.array_equal(soft[:head], w.soft[:head])
     d = np.abs(soft.astype(np.int16) - w.soft.astype(np.int16)).max(axis=1)
     assert (d > 1).mean() < 0.01
+    # --seed: chunks after the first start at the coarse carrier estimate and warm up over 32 Ki samples
+    out2 = tmp_path / "long_seeded.s"
+    r = run([host, "-B", "--shard", "400k", "--seed", "4096", "-o", str(out2), str(wav)])
+    assert b"Locked: Yes" in r.stdout
+    soft2, rep2 = sharded.process_host(raw[: 2 * n], chunk=400_000, warm=32768, overlap=8192, seed_nfft=4096, symrate=72000, bps=16)
+    assert out2.read_bytes() == egress.gate(soft2, rep2["first_lock_symbol"])
+    d2 = np.abs(soft2.astype(np.int16) - w.soft.astype(np.int16)).max(axis=1)
+    assert soft2.shape[0] == w.nsym and (d2 > 1).mean() < 0.01
 
 
 def test_live_pipe_is_demodulated_as_it_arrives(host, oracle_mod, tmp_path):

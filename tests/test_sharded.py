@@ -621,6 +621,17 @@ def test_single_call_c_entry_point_equals_python_handoff(stream, lib):
     assert rep2["nchunks"] == 2 and np.array_equal(got2, w2.soft)          # chunks 0 and 1 are exact
     with pytest.raises(LrptError):
         sharded.process_host(stream, chunk=CHUNK + 4, warm=WARM, overlap=OVERLAP, symrate=72000, bps=16)
+    # seeded chunks (lrpt_shard_plan_t.seed_nfft): the C call runs the same estimator kernel and sets the same field,
+    # so it stays byte-identical to the torch-orchestrated seeded run, with a 32 Ki warm-up
+    want_s = sharded.demod_sharded(raw, N, chunk=CHUNK, warm=32768, overlap=OVERLAP, symrate=72000, bps=16, rrc_order=32,
+                                   interp_factor=5, handoff=True, seed_carrier=True, seed_nfft=4096)
+    got_s, rep_s = sharded.process_host(stream, chunk=CHUNK, warm=32768, overlap=OVERLAP, seed_nfft=4096, symrate=72000,
+                                        bps=16, rrc_order=32, interp_factor=5)
+    assert np.array_equal(got_s, want_s["soft"].cpu().numpy()) and rep_s["aligned"] == 1
+    assert got_s.shape[0] == seq.nsym and float((np.abs(got_s.astype(np.int16) - seq.soft.astype(np.int16)).max(axis=1) > 1).mean()) < 0.01
+    for bad in (1000, 128, 32768):
+        with pytest.raises(LrptError):
+            sharded.process_host(stream, chunk=CHUNK, warm=32768, overlap=OVERLAP, seed_nfft=bad, symrate=72000, bps=16)
 
 
 def random_rows(g, M, C, V, L):
