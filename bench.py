@@ -901,7 +901,8 @@ def bench_sharded(a, cfg, label, rank, world, local, cpu_base):
             from meteor_demod_b200 import symbol_capacity
             out_pinned = torch.empty((symbol_capacity(ne, FS, symrate), 2), dtype=torch.int8, pin_memory=True)
             kwe = dict(chunk=a.chunk, warm=a.warm, overlap=8192, symrate=symrate, bps=bps, rrc_order=order,
-                       interp_factor=interp, device=local, out=out_pinned.numpy())
+                       interp_factor=interp, device=local, out=out_pinned.numpy(),
+                       seed_nfft=a.seed_nfft if a.seed_carrier and 256 <= a.seed_nfft <= 16384 else 0)
             want = res["soft"].cpu().numpy() if ne == N else None
             sd.close()
             sd.eng.raw = None
