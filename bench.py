@@ -69,7 +69,7 @@ def parse():
                     help="sharded: chunks continue from their predecessor's state (sharded.run_handoff; the default)")
     ap.add_argument("--seed-carrier", action="store_true", help="sharded: chunks >= 1 start their Costas NCO at a coarse "
                     "carrier estimate (meteor_demod_b200/acquire.py; opt-in, not what the reference does)")
-    ap.add_argument("--seed-nfft", type=int, default=1 << 17, help="sharded: samples the coarse carrier estimate looks at")
+    ap.add_argument("--seed-nfft", type=int, default=4096, help="sharded: samples the coarse carrier estimate looks at")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-locked", action="store_true", help="skip the steady-state (locked, state carried over) pass")
     ap.add_argument("--no-single", action="store_true", help="skip the single exact stream sub-record")
