@@ -937,6 +937,11 @@ def test_c_level_multi_gpu_equals_one_gpu(stream, lib, tmp_path):
     a, _ = sharded.process_host(short, **kw)
     b, _ = sharded.process_host(short, devices=[0, 1], **kw)
     assert np.array_equal(a, b)
+    # seeded chunks: every rank estimates the carrier of its own rows
+    ks = dict(kw, warm=32768, seed_nfft=4096)
+    s1, _ = sharded.process_host(stream, **ks)
+    s2, r2 = sharded.process_host(stream, devices=[0, 1], **ks)
+    assert np.array_equal(s1, s2) and r2["aligned"] == 1
     host = build.build_host()
     wav = tmp_path / "in.wav"
     wav.write_bytes(synth.wav_header(stream.nbytes) + stream.tobytes())
