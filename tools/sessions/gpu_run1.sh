@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 1: parity suite, A/B of the split recurrence, default bench, ncu captures
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/r2_gpu_tests.log
 echo "== tests done" >&2

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 10 (2 GPUs): C multi-GPU tests after the start-gate change, bench --gpus 2 with c4_weak
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_sharded.py -m gpu -q 2>&1 | tail -5 ) > gpurun_out/r2_gpu_tests10.log
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2b.json 2> gpurun_out/r2_bench_n2b.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 11: chunk / warm-up sweep of the time-sharded stream (throughput vs Tier-S epsilon and boundary agreement)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 : > gpurun_out/r2_c4_sweep.jsonl
 for cw in "262144 150000" "262144 98304" "262144 65536" "131072 98304" "131072 65536" "131072 49152" "98304 65536"; do

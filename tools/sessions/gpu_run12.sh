@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 12: time-sharded stream with the seeded warm-up (coarse carrier estimate): chunk / warm-up / nfft sweep
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 : > gpurun_out/r2_c4_seeded_sweep.jsonl
 for cw in "262144 32768 16384" "262144 49152 16384" "131072 32768 16384" "113360 32768 16384" "131072 49152 16384" "131072 32768 4096" "262144 32768 65536"; do

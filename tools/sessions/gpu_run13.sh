@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 13: seeded c4 after the host-side fixes (vectorised cut targets, batched estimator); sharded tests
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 : > gpurun_out/r2_c4_seeded2.jsonl
 for cw in "262144 32768 8192" "262144 32768 4096" "196608 32768 8192" "131072 32768 8192" "262144 24576 8192"; do

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 14: whole suite, smoke, default bench, reference arm
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8 ) > gpurun_out/r2_gpu_tests14.log
 ( timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 ) > gpurun_out/r2_smoke.log

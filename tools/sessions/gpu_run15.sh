@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 15: ncu launch lists (gpu__time_duration only) of the round-2 bench command, our kernels only
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 K='regex:demod_|shard_|fe_|fir_stage|cursor_'
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/r2_launches_main_step.csv \

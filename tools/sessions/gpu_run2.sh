@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 2: two-warp recurrence -- parity of ws/spec, A/B against the one-warp build, FIR stage tests + bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_fir_stage.py -m gpu -x -q -k "ws or spec or grid or fir_stage or ragged or batch_of" 2>&1 | tail -15 ) > gpurun_out/r2_gpu_tests2.log
 echo "== tests done" >&2

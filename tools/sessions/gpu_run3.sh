@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 3: two-warp recurrence v2 (loop warp scales and mixes)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ws or spec or grid or ragged or batch_of" 2>&1 | tail -15 ) > gpurun_out/r2_gpu_tests3.log
 echo "== tests done" >&2

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 4: whole GPU suite with the new tests, default bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25 ) > gpurun_out/r2_gpu_tests4.log
 echo "== tests done" >&2

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 5 (2 GPUs): bench --gpus 2 incl. the c4 sub-record over two ranks
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
 echo "== bench2 rc=$?" >&2

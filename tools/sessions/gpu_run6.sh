@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 6 (8 GPUs): bench --gpus 4 and --gpus 8 (c4 sub-record over 4 / 8 ranks); short steps
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for n in 4 8; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 5 --warmup 3 --no-single --no-frontend > gpurun_out/r2_bench_n$n.json 2> gpurun_out/r2_bench_n$n.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 9: whole suite, smoke, FIR stage bench + ncu, default bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > gpurun_out/r2_gpu_tests9.log
 echo "== tests done" >&2

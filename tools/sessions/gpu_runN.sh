@@ -1,6 +1,6 @@
 #!/bin/bash
 # bench.py on N GPUs the way the driver launches it: tools/gpu_runN.sh N
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 N=$1
 mkdir -p gpurun_out
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
